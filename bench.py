@@ -1,0 +1,246 @@
+#!/usr/bin/env python
+"""bench.py — output MP/s of the burst super-resolution hot path + merge-stage HBM roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one synthetic burst (BASELINE.json configs[1]: 12 MP RGGB, 8 frames, 2x, full frame)
+through the whole chain (front end -> pyramid tile alignment -> consolidation -> LK flow ->
+kernel params -> robustness -> fused merge).  With N > 1 every rank processes its own burst per
+step (independent bursts shard data-parallel, no data-path collective): weak scaling.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "output_megapixels_per_second"
+UNIT = "MP/s"
+CFG = dict(frames=8, height=3024, width=4032, scale=2)
+CPU_SAMPLE = dict(frames=8, height=768, width=1024)      # bounded sample of the same workload for the CPU arm
+
+
+def merge_bytes_per_px(n, s, gray=False):
+    """compulsory traffic of the fused merge per OUTPUT pixel."""
+    return ((11 if gray else 14) * n + 16) / (s * s) + (8 if gray else 24)
+
+
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(self.samples[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+def hbm_peak():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_cpu_port(steps, warmup):
+    """The reference's CPU path = the oracle port (C + OpenMP, all host threads) on a bounded sample."""
+    import numpy as np
+    from multi_frame_super_resolution_b200.pipeline import default_params
+    from multi_frame_super_resolution_b200.synth import synth_burst
+    from oracle import pyoracle as O
+    cores = O.set_threads(os.cpu_count() or 1)
+    p = default_params()
+    fr, _ = synth_burst(CPU_SAMPLE["frames"], CPU_SAMPLE["height"], CPU_SAMPLE["width"], seed=1234)
+    fr = fr.numpy().view(np.uint16)
+    out_mp = CPU_SAMPLE["height"] * CPU_SAMPLE["width"] * p.scale * p.scale / 1e6
+    for _ in range(warmup):
+        O.run_pipeline(fr, p)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.run_pipeline(fr, p)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    sample = f"{CPU_SAMPLE['frames']} frames of {CPU_SAMPLE['width']}x{CPU_SAMPLE['height']} RGGB (1/15.5 of the 12 MP burst), whole chain"
+    return out_mp / dt, dt * 1e3, cores, sample
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = f"synthetic {CFG['width']}x{CFG['height']} (12 MP) RGGB burst, {CFG['frames']} frames, {CFG['scale']}x, full frame"
+    config = {"workload": workload, "frames": CFG["frames"], "raw": [CFG["width"], CFG["height"]], "scale": CFG["scale"],
+              "bursts_per_step": max(world, 1), "parallelism": f"dp{max(world, 1)} (independent bursts, no data-path collective)",
+              "l2": "inputs larger than L2 (raw 195 MB + flow 780 MB + masks 390 MB per burst vs 126 MB L2)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = max(1, min(args.steps, 3)); warm = min(args.warmup, 1)
+        val, ms, cores, sample = run_cpu_port(steps, warm)
+        line = {"impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+                "warmup": warm, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": round(val, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": round(val, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "reference CPU path = oracle port (C/OpenMP); the reference's kernels have no CPU implementation and its OpenCV superres host path is not installable (DESIGN.md)"}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from multi_frame_super_resolution_b200.pipeline import BurstSuperResolution, default_params
+    from multi_frame_super_resolution_b200.synth import synth_burst
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, h, w, s = CFG["frames"], CFG["height"], CFG["width"], CFG["scale"]
+    p = default_params()
+    sr = BurstSuperResolution(p, device=local_rank, max_width=w, max_height=h, max_frames=n)
+    frames, _ = synth_burst(n, h, w, seed=1234 + rank, device=dev)          # burst b uses seed 1234 + b
+    ow, oh = sr.output_size(w, h)
+    out_dev = torch.empty((oh, ow, 3), dtype=torch.float32, device=dev)
+    out_mp = ow * oh / 1e6
+    stream = torch.cuda.ExternalStream(sr.stream, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_resident():
+        sr.set_input(frames)                    # D2D staging into the handle's frame stack (part of the step)
+        sr.next_frame(out=out_dev)
+
+    # ---------------- device-resident timing (value)
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    merge_ms, launches, stage_acc = [], 0, {}
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+        launches += sr.launch_count()
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    # per-stage device time of the LAST step (CUDA events on the launching stream), merge averaged separately below
+    stage_last = sr.stage_ms()
+    # merge kernel: average launch duration over `steps` launches, each preceded by the rest of the chain
+    for _ in range(args.steps):
+        step_resident()
+        merge_ms.append(sr.stage_ms()["merge"])
+    barrier()
+    clocks = sampler.summary()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = out_mp * world / (ms_step / 1e3)
+
+    # ---------------- end-to-end through the C ABI with HOST buffers (e2e)
+    host_in = torch.empty((n, h, w), dtype=torch.int16, pin_memory=True)
+    host_in.copy_(frames)
+    host_out = torch.empty((oh, ow, 3), dtype=torch.float32, pin_memory=True)
+    host_np = host_in.numpy().view(np.uint16)
+
+    def step_e2e():
+        sr.set_input(host_np)                   # H2D of the 8 raw frames inside the timed region
+        sr.next_frame(out=host_out, host=True)  # D2H of the float3 image + stream sync
+
+    e2e_steps = max(2, min(args.steps, 5))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize(dev)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    t2 = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_val = out_mp * world / (float(t2.item()) / 1e3)
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        bpp = merge_bytes_per_px(n, s)
+        mm = float(np.mean(merge_ms))
+        achieved = bpp * ow * oh / (mm / 1e3) / 1e9
+        traffic = None
+        tf = ROOT / "profiles" / "merge_traffic.json"
+        if tf.exists():
+            try:
+                traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config,
+                "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": int(n * h * w * 2), "d2h_bytes_per_step": int(ow * oh * 12),
+                        "ms_per_step": round(float(t2.item()), 3), "timed": "host wall clock around mfsr_set_frames(host)+mfsr_run(host out), max over ranks"},
+                "gpu_launches": int(launches),
+                "roofline": {"kernel": "merge (mfsr_stage_merge)", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                             "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                             "bytes_per_output_px": bpp, "ms_per_launch": round(mm, 4)},
+                "stage_ms": {k: round(v, 3) for k, v in stage_last.items()},
+                "clocks": clocks}
+        if not args.no_cpu_baseline and world == 1:
+            val, ms, cores, sample = run_cpu_port(1, 0)
+            line["cpu_baseline"] = {"value": round(val, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms": round(ms, 1)}
+        print(json.dumps(line))
+    sr.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

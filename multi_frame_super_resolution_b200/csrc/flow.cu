@@ -1,0 +1,177 @@
+// flow.cu — dense flow from the tile-shift grid and Lucas-Kanade refinement.
+//
+// lk_iteration_kernel fuses WarpingKernel (opticalFlow.cu:28), ComputeDerivativesKernel (:97)
+// and lucasKanadeOptim (:190) into one launch per sweep: the warped image and the three
+// derivative planes (4 x 4 B/px of HBM write + (2h+1)^2 x 3 uncoalesced re-reads per pixel in
+// the reference) never leave shared memory; the window sums are separable (row sums, then
+// column sums) instead of two full (2h+1)^2 passes per pixel.
+// HBM traffic per sweep: ref gray 4 B + moved gray (gather, ~4 B) + flow 8 B in, 8 B out.
+#include "common.cuh"
+
+namespace mfsr {
+
+// CreateFlowFieldFromTiles (opticalFlow.cu:48-93)
+__global__ void __launch_bounds__(256)
+flow_from_tiles_kernel(const float2* __restrict__ tiles, int64_t tile_pitch, int tilesX, int tilesY,
+                       float2* __restrict__ flow, int64_t flow_pitch, int w, int h, float bsx, float bsy, float rot)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const float cr = cosf(rot), sr = sinf(rot);
+    float sx = cr * -bsx - sr * -bsy;
+    float sy = sr * -bsx + cr * -bsy;
+    const float pcx = (float)(x - w / 2), pcy = (float)(y - h / 2);
+    sx += cr * pcx - sr * pcy - pcx;
+    sy += sr * pcx + cr * pcy - pcy;
+    const TexAxis ax = tex_axis(tex_coord((float)x + 0.5f, w, tilesX), tilesX);
+    const TexAxis ay = tex_axis(tex_coord((float)y + 0.5f, h, tilesY), tilesY);
+    const float2 t00 = row_ptr(tiles, tile_pitch, ay.i0)[ax.i0], t10 = row_ptr(tiles, tile_pitch, ay.i0)[ax.i1];
+    const float2 t01 = row_ptr(tiles, tile_pitch, ay.i1)[ax.i0], t11 = row_ptr(tiles, tile_pitch, ay.i1)[ax.i1];
+    sx += tex_mix(t00.x, t10.x, t01.x, t11.x, ax.a, ay.a);
+    sy += tex_mix(t00.y, t10.y, t01.y, t11.y, ax.a, ay.a);
+    row_ptr(flow, flow_pitch, y)[x] = make_float2(sx, sy);
+}
+
+constexpr int LTW = 32, LTH = 16, LHW_MAX = 4;
+constexpr int LRW = LTW + 2 * LHW_MAX, LRH = LTH + 2 * LHW_MAX;     // derivative region
+constexpr int LWW = LRW + 4, LWH = LRH + 4;                           // warped / source region
+
+// closed-form 2x2 SVD pseudo-inverse of the window matrix [[a,b],[c,d]] (opticalFlow.cu:236-292),
+// including the fminf(sigma1, sigma1) quirk (:255).  Returns false when the reference returns early.
+__device__ __forceinline__ bool lk_pinv(float a, float b, float c, float d, float minDet, float inv[4])
+{
+    const float theta = 0.5f * atan2f(2.0f * a * c + 2.0f * b * d, a * a + b * b - c * c - d * d);
+    const float ct = cosf(theta), st = sinf(theta);
+    const float UT0 = ct, UT2 = -st, UT1 = st, UT3 = ct;
+    const float S1 = a * a + b * b + c * c + d * d;
+    const float S2 = sqrtf((a * a + b * b - c * c - d * d) * (a * a + b * b - c * c - d * d) + 4 * (a * c + b * d) * (a * c + b * d));
+    float sigma1 = sqrtf((S1 + S2) / 2), sigma2 = sqrtf((S1 - S2) / 2);
+    const float smin = fminf(sigma1, sigma1);
+    if (smin < minDet) return false;
+    sigma1 = sigma1 != 0 ? 1.0f / sigma1 : 0;
+    sigma2 = sigma2 != 0 ? 1.0f / sigma2 : 0;
+    const float eps = 0.5f * atan2f(2.0f * a * b + 2.0f * c * d, a * a - b * b + c * c - d * d);
+    const float ce = cosf(eps), se = sinf(eps);
+    float s11 = (a * ct + c * st) * ce + (b * ct + d * st) * se;
+    float s22 = (a * st - c * ct) * se + (-b * st + d * ct) * ce;
+    s11 = s11 > 0.0f ? 1.0f : s11 < 0 ? -1.0f : 0.0f;
+    s22 = s22 > 0.0f ? 1.0f : s22 < 0 ? -1.0f : 0.0f;
+    const float V0 = s11 * ce, V1 = -s22 * se, V2 = s11 * se, V3 = s22 * ce;
+    const float m0 = sigma1 * UT0 + 0.0f * UT2, m1 = sigma1 * UT1 + 0.0f * UT3;
+    const float m2 = 0.0f * UT0 + sigma2 * UT2, m3 = 0.0f * UT1 + sigma2 * UT3;
+    inv[0] = V0 * m0 + V1 * m2; inv[1] = V0 * m1 + V1 * m3;
+    inv[2] = V2 * m0 + V3 * m2; inv[3] = V2 * m1 + V3 * m3;
+    return true;
+}
+
+__global__ void __launch_bounds__(256)
+lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov, int64_t img_pitch,
+                    const float2* __restrict__ flow_in, float2* __restrict__ flow_out, int64_t flow_pitch,
+                    int w, int h, int hw, float minDet)
+{
+    __shared__ float s_src[LWH][LWW];
+    __shared__ float s_wrp[LWH][LWW];
+    __shared__ float s_ix[LRH][LRW], s_iy[LRH][LRW], s_it[LRH][LRW];
+    __shared__ float s_h[5][LRH][LTW];
+    const int x0 = blockIdx.x * LTW, y0 = blockIdx.y * LTH;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    const int RW = LTW + 2 * hw, RH = LTH + 2 * hw, WW = RW + 4, WH = RH + 4;
+    const int ox = x0 - hw - 2, oy = y0 - hw - 2;         // global coordinate of s_src[0][0]
+
+    // 1. source + warped moved image (WarpingKernel) on the haloed region, clamp addressing
+    for (int i = tid; i < WW * WH; i += nthr) {
+        const int ly = i / WW, lx = i - ly * WW;
+        const int gx = clampi(ox + lx, 0, w - 1), gy = clampi(oy + ly, 0, h - 1);
+        s_src[ly][lx] = row_ptr(ref, img_pitch, gy)[gx];
+        const float2 f = row_ptr(flow_in, flow_pitch, gy)[gx];
+        const TexAxis ax = tex_axis(tex_coord((float)gx + 0.5f + f.x, w, w), w);
+        const TexAxis ay = tex_axis(tex_coord((float)gy + 0.5f + f.y, h, h), h);
+        const float* r0 = row_ptr(mov, img_pitch, ay.i0);
+        const float* r1 = row_ptr(mov, img_pitch, ay.i1);
+        s_wrp[ly][lx] = tex_mix(r0[ax.i0], r0[ax.i1], r1[ax.i0], r1[ax.i1], ax.a, ay.a);
+    }
+    __syncthreads();
+    // 2. derivatives (ComputeDerivativesKernel): 5-tap (1,-8,0,8,-1)/12 on source and warped, clamp
+    for (int i = tid; i < RW * RH; i += nthr) {
+        const int ry = i / RW, rx = i - ry * RW;
+        const int gx = clampi(x0 - hw + rx, 0, w - 1), gy = clampi(y0 - hw + ry, 0, h - 1);
+        const int cy = gy - oy, cx = gx - ox;
+        const int xm2 = clampi(gx - 2, 0, w - 1) - ox, xm1 = clampi(gx - 1, 0, w - 1) - ox;
+        const int xp1 = clampi(gx + 1, 0, w - 1) - ox, xp2 = clampi(gx + 2, 0, w - 1) - ox;
+        const int ym2 = clampi(gy - 2, 0, h - 1) - oy, ym1 = clampi(gy - 1, 0, h - 1) - oy;
+        const int yp1 = clampi(gy + 1, 0, h - 1) - oy, yp2 = clampi(gy + 2, 0, h - 1) - oy;
+        float t0, t1;
+        t0 = s_src[cy][xp2]; t0 -= s_src[cy][xp1] * 8.0f; t0 += s_src[cy][xm1] * 8.0f; t0 -= s_src[cy][xm2]; t0 /= 12.0f;
+        t1 = s_wrp[cy][xp2]; t1 -= s_wrp[cy][xp1] * 8.0f; t1 += s_wrp[cy][xm1] * 8.0f; t1 -= s_wrp[cy][xm2]; t1 /= 12.0f;
+        s_ix[ry][rx] = (t0 + t1) * 0.5f;
+        // texSource = warped, texTarget = reference: the stencil above is MINUS the derivative, so
+        // Iz = warped - ref is the sign that makes `shift += UV` descend (restated host)
+        s_it[ry][rx] = s_wrp[cy][cx] - s_src[cy][cx];
+        t0 = s_src[yp2][cx]; t0 -= s_src[yp1][cx] * 8.0f; t0 += s_src[ym1][cx] * 8.0f; t0 -= s_src[ym2][cx]; t0 /= 12.0f;
+        t1 = s_wrp[yp2][cx]; t1 -= s_wrp[yp1][cx] * 8.0f; t1 += s_wrp[ym1][cx] * 8.0f; t1 -= s_wrp[ym2][cx]; t1 /= 12.0f;
+        s_iy[ry][rx] = (t0 + t1) * 0.5f;
+    }
+    __syncthreads();
+    // 3. row sums of the five products over [-hw, hw]
+    for (int i = tid; i < LTW * RH; i += nthr) {
+        const int ry = i / LTW, lx = i - ry * LTW;
+        float sxx = 0.f, sxy = 0.f, syy = 0.f, sxt = 0.f, syt = 0.f;
+        for (int k = 0; k <= 2 * hw; k++) {
+            const float dx = s_ix[ry][lx + k], dy = s_iy[ry][lx + k], dt = s_it[ry][lx + k];
+            sxx += dx * dx; sxy += dx * dy; syy += dy * dy; sxt += dx * dt; syt += dy * dt;
+        }
+        s_h[0][ry][lx] = sxx; s_h[1][ry][lx] = sxy; s_h[2][ry][lx] = syy; s_h[3][ry][lx] = sxt; s_h[4][ry][lx] = syt;
+    }
+    __syncthreads();
+    // 4. column sums, pseudo-inverse, update (lucasKanadeOptim)
+    for (int ly = threadIdx.y; ly < LTH; ly += blockDim.y) {
+        const int lx = threadIdx.x, gx = x0 + lx, gy = y0 + ly;
+        if (gx >= w || gy >= h) continue;
+        float2 f = row_ptr(flow_in, flow_pitch, gy)[gx];
+        if (!(gx < hw || gx >= w - hw || gy < hw || gy >= h - hw)) {
+            float sxx = 0.f, sxy = 0.f, syy = 0.f, sxt = 0.f, syt = 0.f;
+            for (int k = 0; k <= 2 * hw; k++) {
+                sxx += s_h[0][ly + k][lx]; sxy += s_h[1][ly + k][lx]; syy += s_h[2][ly + k][lx];
+                sxt += s_h[3][ly + k][lx]; syt += s_h[4][ly + k][lx];
+            }
+            float inv[4];
+            if (lk_pinv(sxx, sxy, sxy, syy, minDet, inv)) {
+                float u = inv[0] * sxt + inv[1] * syt;
+                float v = inv[2] * sxt + inv[3] * syt;
+                u = isnan(u) ? 0.f : u;
+                v = isnan(v) ? 0.f : v;
+                f.x += u; f.y += v;
+            }
+        }
+        row_ptr(flow_out, flow_pitch, gy)[gx] = f;
+    }
+}
+
+}  // namespace mfsr
+
+using namespace mfsr;
+
+extern "C" int mfsr_stage_flow_from_tiles(const float* tile_shift, int64_t tile_pitch, int tilesX, int tilesY, int tile_size,
+                                          float* flow, int64_t flow_pitch, int width, int height,
+                                          float base_shift_x, float base_shift_y, float base_rotation, void* stream)
+{
+    (void)tile_size;
+    if (!tile_shift || !flow || tilesX < 1 || tilesY < 1 || width < 1 || height < 1) return MFSR_E_INVALID;
+    dim3 b(32, 8), g(cdiv(width, 32), cdiv(height, 8));
+    flow_from_tiles_kernel<<<g, b, 0, (cudaStream_t)stream>>>((const float2*)tile_shift, tile_pitch, tilesX, tilesY, (float2*)flow, flow_pitch,
+                                                             width, height, base_shift_x, base_shift_y, base_rotation);
+    MFSR_LAUNCH_CHECK();
+    return MFSR_OK;
+}
+
+extern "C" int mfsr_stage_lk_iteration(const float* ref, const float* mov, int64_t img_pitch, const float* flow_in, float* flow_out,
+                                       int64_t flow_pitch, int width, int height, int half_window, float min_det, void* stream)
+{
+    if (!ref || !mov || !flow_in || !flow_out || flow_in == flow_out || width < 1 || height < 1) return MFSR_E_INVALID;
+    if (half_window < 1 || half_window > LHW_MAX) return MFSR_E_INVALID;
+    dim3 b(LTW, 8), g(cdiv(width, LTW), cdiv(height, LTH));
+    lk_iteration_kernel<<<g, b, 0, (cudaStream_t)stream>>>(ref, mov, img_pitch, (const float2*)flow_in, (float2*)flow_out, flow_pitch,
+                                                          width, height, half_window, min_det);
+    MFSR_LAUNCH_CHECK();
+    return MFSR_OK;
+}

@@ -1,0 +1,315 @@
+// frontend.cu — per-frame front end: Bayer sub-sampling, demosaic, tracking image, pyramid.
+//
+// Compiled with -fmad=false (see build.py): the 7-bit tracking image feeds the
+// integer block matcher, so its fp32 arithmetic must round exactly like a strict
+// IEEE evaluation of the same formulas (oracle/mfsr_oracle.c) — then the integer
+// tile shifts are bit-exact by construction.  These kernels are HBM-bound
+// (2 B in, 4..12 B out per pixel); the lost FMA contraction costs nothing.
+//
+// Replaces deBayersSubSample3 (DeBayerKernels.cu:244), deBayerGreenKernel (:55) +
+// deBayerRedBlueKernel (:153) — fused: the green plane lives in shared memory
+// instead of a second launch reading the first one's HBM output — and the absent
+// host's B/W + Gaussian (gaussin_filter_1D, main.cpp:370) + resize steps.
+#include "common.cuh"
+
+namespace mfsr {
+
+// ---------------------------------------------------------------- subsample3
+__global__ void __launch_bounds__(256)
+subsample3_kernel(const uint16_t* __restrict__ raw, int64_t raw_pitch, float* __restrict__ out, int64_t out_pitch,
+                  float factor, int dimX, int dimY, Cfa cfa)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dimX || y >= dimY) return;
+    // one 32-bit load per Bayer row: two neighbouring u16 samples
+    const uint32_t r0 = *(const uint32_t*)(row_ptr(raw, raw_pitch, 2 * y) + 2 * x);
+    const uint32_t r1 = *(const uint32_t*)(row_ptr(raw, raw_pitch, 2 * y + 1) + 2 * x);
+    const float v[4] = {(float)(r0 & 0xffffu), (float)(r0 >> 16), (float)(r1 & 0xffffu), (float)(r1 >> 16)};
+    float px[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ix = 0; ix < 2; ix++)
+#pragma unroll
+        for (int iy = 0; iy < 2; iy++) {
+            const int col = cfa.c[iy * 2 + ix];
+            const float r = v[iy * 2 + ix];
+            if (col == MFSR_GREEN) px[1] += r * factor * 0.5f;      // two greens per quad (:267)
+            else if (col == MFSR_RED) px[0] = r * factor;
+            else if (col == MFSR_BLUE) px[2] = r * factor;
+        }
+    float* o = row_ptr(out, out_pitch, y) + 3 * x;
+    o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
+}
+
+// ---------------------------------------------------------------- demosaic tile
+// Shared-memory staged demosaic of a TW x TH tile grown by HR pixels on each side.
+//   raw plane : region grown by HR+3 (green needs +-2 of its own +-1 halo)
+//   green     : region grown by HR+1
+// Pixels in the 2-px image border (never written by the reference) are 0.
+template <int TW, int TH, int HR>
+struct DemosaicTile {
+    static constexpr int RW = TW + 2 * (HR + 3), RH = TH + 2 * (HR + 3);
+    static constexpr int GW = TW + 2 * (HR + 1), GH = TH + 2 * (HR + 1);
+    float raw[RH][RW];
+    float grn[GH][GW];
+};
+
+__device__ __forceinline__ float rawc(float v, int c, const F3& black, const F3& scale) { return (v - black.v[c]) * scale.v[c]; }
+
+template <int TW, int TH, int HR>
+__device__ void demosaic_stage(DemosaicTile<TW, TH, HR>& S, const uint16_t* __restrict__ raw, int64_t raw_pitch,
+                               int w, int h, int x0, int y0, const Cfa& cfa, const F3& black, const F3& scale)
+{
+    using DT = DemosaicTile<TW, TH, HR>;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    for (int i = tid; i < DT::RW * DT::RH; i += nthr) {
+        const int ry = i / DT::RW, rx = i - ry * DT::RW;
+        const int gx = clampi(x0 - (HR + 3) + rx, 0, w - 1), gy = clampi(y0 - (HR + 3) + ry, 0, h - 1);
+        S.raw[ry][rx] = (float)row_ptr(raw, raw_pitch, gy)[gx];
+    }
+    __syncthreads();
+    // green (deBayerGreenKernel, DeBayerKernels.cu:55-149)
+    for (int i = tid; i < DT::GW * DT::GH; i += nthr) {
+        const int qy = i / DT::GW, qx = i - qy * DT::GW;
+        const int gx = x0 - (HR + 1) + qx, gy = y0 - (HR + 1) + qy;
+        float g = 0.f;
+        if (gx >= 2 && gx < w - 2 && gy >= 2 && gy < h - 2) {
+            const int ry = qy + 2, rx = qx + 2;
+            const int col = cfa.c[(gy & 1) * 2 + (gx & 1)];
+            if (col == MFSR_GREEN) g = rawc(S.raw[ry][rx], 1, black, scale);
+            else if (col == MFSR_RED || col == MFSR_BLUE) {
+                const float p = rawc(S.raw[ry][rx], col, black, scale);
+                const float xm2 = rawc(S.raw[ry][rx - 2], col, black, scale), xm1 = rawc(S.raw[ry][rx - 1], 1, black, scale);
+                const float xp1 = rawc(S.raw[ry][rx + 1], 1, black, scale), xp2 = rawc(S.raw[ry][rx + 2], col, black, scale);
+                const float ym2 = rawc(S.raw[ry - 2][rx], col, black, scale), ym1 = rawc(S.raw[ry - 1][rx], 1, black, scale);
+                const float yp1 = rawc(S.raw[ry + 1][rx], 1, black, scale), yp2 = rawc(S.raw[ry + 2][rx], col, black, scale);
+                const float gradX = 0.5f * fabsf(xp1 - xm1), gradY = 0.5f * fabsf(yp1 - ym1);
+                const float lapX = 0.25f * fabsf(2.0f * p - xm2 - xp2), lapY = 0.25f * fabsf(2.0f * p - ym2 - yp2);
+                const float ipX = 0.125f * (-xm2 + 4.0f * xm1 + 2.0f * p + 4.0f * xp1 - xp2);
+                const float ipY = 0.125f * (-ym2 + 4.0f * ym1 + 2.0f * p + 4.0f * yp1 - yp2);
+                const float wgt = (gradY + lapY) / (gradX + gradY + lapX + lapY + 0.000000001f);
+                g = wgt * ipX + (1.0f - wgt) * ipY;
+            }
+        }
+        S.grn[qy][qx] = g;
+    }
+    __syncthreads();
+}
+
+// red/blue of one pixel (deBayerRedBlueKernel, :153-231); (lx,ly) relative to the tile origin, in [-HR, T+HR)
+template <int TW, int TH, int HR>
+__device__ __forceinline__ void demosaic_px(const DemosaicTile<TW, TH, HR>& S, int lx, int ly, int gx, int gy, int w, int h,
+                                            const Cfa& cfa, const F3& black, const F3& scale, float& r, float& g, float& b)
+{
+    r = g = b = 0.f;
+    if (gx < 2 || gx >= w - 2 || gy < 2 || gy >= h - 2) return;
+    const int qx = lx + HR + 1, qy = ly + HR + 1, rx = lx + HR + 3, ry = ly + HR + 3;
+#define RAWX(dx, dy, c) rawc(S.raw[ry + (dy)][rx + (dx)], c, black, scale)
+#define GRNX(dx, dy) S.grn[qy + (dy)][qx + (dx)]
+    const int col = cfa.c[(gy & 1) * 2 + (gx & 1)];
+    const int row = cfa.c[(gy & 1) * 2 + ((gx + 1) & 1)];
+    g = GRNX(0, 0);
+    if (col == MFSR_GREEN) {
+        if (row == MFSR_RED) {
+            r = g + 0.5f * ((RAWX(-1, 0, 0) - GRNX(-1, 0)) + (RAWX(1, 0, 0) - GRNX(1, 0)));
+            b = g + 0.5f * ((RAWX(0, -1, 2) - GRNX(0, -1)) + (RAWX(0, 1, 2) - GRNX(0, 1)));
+        } else {
+            b = g + 0.5f * ((RAWX(-1, 0, 2) - GRNX(-1, 0)) + (RAWX(1, 0, 2) - GRNX(1, 0)));
+            r = g + 0.5f * ((RAWX(0, -1, 0) - GRNX(0, -1)) + (RAWX(0, 1, 0) - GRNX(0, 1)));
+        }
+    } else if (col == MFSR_RED) {
+        r = RAWX(0, 0, 0);
+        b = g + 0.25f * ((RAWX(-1, -1, 2) - GRNX(-1, -1)) + (RAWX(1, -1, 2) - GRNX(1, -1)) + (RAWX(1, 1, 2) - GRNX(1, 1)) + (RAWX(-1, 1, 2) - GRNX(-1, 1)));
+    } else if (col == MFSR_BLUE) {
+        b = RAWX(0, 0, 2);
+        r = g + 0.25f * ((RAWX(-1, -1, 0) - GRNX(-1, -1)) + (RAWX(1, -1, 0) - GRNX(1, -1)) + (RAWX(1, 1, 0) - GRNX(1, 1)) + (RAWX(-1, 1, 0) - GRNX(-1, 1)));
+    }
+#undef RAWX
+#undef GRNX
+}
+
+constexpr int DTW = 32, DTH = 16;
+
+__global__ void __launch_bounds__(256)
+demosaic_kernel(const uint16_t* __restrict__ raw, int64_t raw_pitch, float* __restrict__ rgb, int64_t rgb_pitch,
+                int w, int h, Cfa cfa, F3 black, F3 scale)
+{
+    __shared__ DemosaicTile<DTW, DTH, 0> S;
+    const int x0 = blockIdx.x * DTW, y0 = blockIdx.y * DTH;
+    demosaic_stage(S, raw, raw_pitch, w, h, x0, y0, cfa, black, scale);
+    for (int ly = threadIdx.y; ly < DTH; ly += blockDim.y) {
+        const int gx = x0 + threadIdx.x, gy = y0 + ly;
+        if (gx >= w || gy >= h) continue;
+        float r, g, b;
+        demosaic_px(S, (int)threadIdx.x, ly, gx, gy, w, h, cfa, black, scale, r, g, b);
+        float* o = row_ptr(rgb, rgb_pitch, gy) + 3 * gx;
+        o[0] = r; o[1] = g; o[2] = b;
+    }
+}
+
+// ---------------------------------------------------------------- tracking image
+constexpr int MAX_TAPS = 9;
+struct Taps { float t[MAX_TAPS]; int n; };
+
+template <int R>
+__global__ void __launch_bounds__(256)
+tracking_kernel(const uint16_t* __restrict__ raw, int64_t raw_pitch, float* __restrict__ gray, int64_t gray_pitch,
+                uint8_t* __restrict__ gray_q, int64_t gq_pitch, int w, int h, Cfa cfa, F3 black, F3 scale, Taps taps, float qmax)
+{
+    __shared__ DemosaicTile<DTW, DTH, R> S;
+    __shared__ float lum[DTH + 2 * R][DTW + 2 * R];
+    __shared__ float hb[DTH + 2 * R][DTW];
+    const int x0 = blockIdx.x * DTW, y0 = blockIdx.y * DTH;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    demosaic_stage(S, raw, raw_pitch, w, h, x0, y0, cfa, black, scale);
+    constexpr int LW = DTW + 2 * R, LH = DTH + 2 * R;
+    for (int i = tid; i < LW * LH; i += nthr) {
+        const int ly = i / LW - R, lx = i % LW - R;
+        float r, g, b;
+        demosaic_px(S, lx, ly, x0 + lx, y0 + ly, w, h, cfa, black, scale, r, g, b);
+        // out-of-image pixels are never read (clamped indices below)
+        lum[ly + R][lx + R] = 0.25f * r + 0.5f * g + 0.25f * b;
+    }
+    __syncthreads();
+    // horizontal pass, clamp border: index = clamp(x+k-c, 0, w-1)
+    for (int i = tid; i < DTW * LH; i += nthr) {
+        const int ry = i / DTW, lx = i - ry * DTW;
+        const int gx = x0 + lx;
+        float acc = 0.f;
+        for (int k = 0; k < taps.n; k++) {
+            const int sx = clampi(gx + k - R, 0, w - 1) - x0 + R;
+            acc += taps.t[k] * lum[ry][clampi(sx, 0, LW - 1)];
+        }
+        hb[ry][lx] = acc;
+    }
+    __syncthreads();
+    for (int ly = threadIdx.y; ly < DTH; ly += blockDim.y) {
+        const int lx = threadIdx.x, gx = x0 + lx, gy = y0 + ly;
+        if (gx >= w || gy >= h) continue;
+        float acc = 0.f;
+        for (int k = 0; k < taps.n; k++) {
+            const int sy = clampi(gy + k - R, 0, h - 1) - y0 + R;
+            acc += taps.t[k] * hb[clampi(sy, 0, LH - 1)][lx];
+        }
+        if (gray) row_ptr(gray, gray_pitch, gy)[gx] = acc;
+        if (gray_q) {
+            float q = floorf(acc * qmax + 0.5f);
+            q = fminf(fmaxf(q, 0.0f), qmax);
+            row_ptr(gray_q, gq_pitch, gy)[gx] = (uint8_t)q;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- pyramid
+__global__ void __launch_bounds__(256)
+pyramid_down_kernel(const uint8_t* __restrict__ in, int64_t in_pitch, uint8_t* __restrict__ out, int64_t out_pitch, int ow, int oh)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= ow || y >= oh) return;
+    const uint8_t* r0 = row_ptr(in, in_pitch, 2 * y) + 2 * x;
+    const uint8_t* r1 = row_ptr(in, in_pitch, 2 * y + 1) + 2 * x;
+    const int s = (int)r0[0] + (int)r0[1] + (int)r1[0] + (int)r1[1];
+    row_ptr(out, out_pitch, y)[x] = (uint8_t)((s + 2) >> 2);
+}
+
+// ---------------------------------------------------------------- fallback upsample
+__global__ void __launch_bounds__(256)
+fallback_upsample_kernel(const float* __restrict__ rgb, int64_t rgb_pitch, int w, int h,
+                         float* __restrict__ out, int64_t out_pitch, mfsr_merge_geom g)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= g.out_w || y >= g.out_h) return;
+    const float u = __fdiv_rn((float)(x + g.org_x) + 0.5f, (float)g.scale), v = __fdiv_rn((float)(y + g.org_y) + 0.5f, (float)g.scale);
+    const TexAxis tx = tex_axis(u, w), ty = tex_axis(v, h);
+    const float* r0 = row_ptr(rgb, rgb_pitch, ty.i0);
+    const float* r1 = row_ptr(rgb, rgb_pitch, ty.i1);
+    float* o = row_ptr(out, out_pitch, y) + 3 * x;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+        o[c] = tex_mix(r0[3 * tx.i0 + c], r0[3 * tx.i1 + c], r1[3 * tx.i0 + c], r1[3 * tx.i1 + c], tx.a, ty.a);
+}
+
+// host mirror of gaussin_filter_1D (main.cpp:370-391)
+static int gauss_taps(float sigma, float* taps)
+{
+    if (sigma <= 0) { for (int i = 0; i < 9; i++) taps[i] = (i == 4) ? 1.0f : 0.0f; return 9; }
+    int size = (int)(sigma / 0.6f - 0.4f) * 2 + 1 + 2;
+    if (size > 99) size = 99;
+    if (size > MAX_TAPS) return -1;
+    const int center = size / 2;
+    for (int i = 0; i < size; i++) { const int x = i - center; taps[i] = (float)(exp(-(x * x) / (2 * sigma * sigma))); }
+    float sum = 0;
+    for (int i = 0; i < size; i++) sum += taps[i];
+    for (int i = 0; i < size; i++) taps[i] /= sum;
+    return size;
+}
+
+}  // namespace mfsr
+
+using namespace mfsr;
+
+static Cfa mk_cfa(const int cfa[4]) { Cfa c; for (int i = 0; i < 4; i++) c.c[i] = cfa[i]; return c; }
+static F3 mk_f3(const float v[3]) { F3 f; for (int i = 0; i < 3; i++) f.v[i] = v[i]; return f; }
+
+extern "C" int mfsr_stage_subsample3(const uint16_t* raw, int64_t raw_pitch, float* rgb_half, int64_t rgb_pitch,
+                                     float maxVal, int dimX, int dimY, const int cfa[4], void* stream)
+{
+    if (!raw || !rgb_half || !cfa || dimX <= 0 || dimY <= 0 || (raw_pitch & 3) || ((uintptr_t)raw & 3)) return MFSR_E_INVALID;
+    dim3 b(32, 8), g(cdiv(dimX, 32), cdiv(dimY, 8));
+    subsample3_kernel<<<g, b, 0, (cudaStream_t)stream>>>(raw, raw_pitch, rgb_half, rgb_pitch, 1.0f / maxVal, dimX, dimY, mk_cfa(cfa));
+    MFSR_LAUNCH_CHECK();
+    return MFSR_OK;
+}
+
+extern "C" int mfsr_stage_demosaic(const uint16_t* raw, int64_t raw_pitch, float* rgb, int64_t rgb_pitch,
+                                   int width, int height, const int cfa[4], const float black[3], const float scale[3], void* stream)
+{
+    if (!raw || !rgb || !cfa || !black || !scale || width <= 0 || height <= 0) return MFSR_E_INVALID;
+    dim3 b(DTW, 8), g(cdiv(width, DTW), cdiv(height, DTH));
+    demosaic_kernel<<<g, b, 0, (cudaStream_t)stream>>>(raw, raw_pitch, rgb, rgb_pitch, width, height, mk_cfa(cfa), mk_f3(black), mk_f3(scale));
+    MFSR_LAUNCH_CHECK();
+    return MFSR_OK;
+}
+
+extern "C" int mfsr_stage_tracking_image(const uint16_t* raw, int64_t raw_pitch, float* gray, int64_t gray_pitch,
+                                         uint8_t* gray_q, int64_t gray_q_pitch, int width, int height, const int cfa[4],
+                                         const float black[3], const float scale[3], float sigma, int track_bits, void* stream)
+{
+    if (!raw || !cfa || !black || !scale || width <= 0 || height <= 0 || track_bits < 1 || track_bits > 8) return MFSR_E_INVALID;
+    Taps t;
+    t.n = gauss_taps(sigma, t.t);
+    if (t.n < 0) return MFSR_E_INVALID;
+    const float qmax = (float)((1 << track_bits) - 1);
+    dim3 b(DTW, 8), g(cdiv(width, DTW), cdiv(height, DTH));
+    const Cfa c = mk_cfa(cfa); const F3 bl = mk_f3(black), sc = mk_f3(scale);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (t.n / 2) {
+        case 1: tracking_kernel<1><<<g, b, 0, st>>>(raw, raw_pitch, gray, gray_pitch, gray_q, gray_q_pitch, width, height, c, bl, sc, t, qmax); break;
+        case 2: tracking_kernel<2><<<g, b, 0, st>>>(raw, raw_pitch, gray, gray_pitch, gray_q, gray_q_pitch, width, height, c, bl, sc, t, qmax); break;
+        case 3: tracking_kernel<3><<<g, b, 0, st>>>(raw, raw_pitch, gray, gray_pitch, gray_q, gray_q_pitch, width, height, c, bl, sc, t, qmax); break;
+        case 4: tracking_kernel<4><<<g, b, 0, st>>>(raw, raw_pitch, gray, gray_pitch, gray_q, gray_q_pitch, width, height, c, bl, sc, t, qmax); break;
+        default: return MFSR_E_INVALID;
+    }
+    MFSR_LAUNCH_CHECK();
+    return MFSR_OK;
+}
+
+extern "C" int mfsr_stage_pyramid_down(const uint8_t* in, int64_t in_pitch, int in_w, int in_h, uint8_t* out, int64_t out_pitch, void* stream)
+{
+    if (!in || !out || in_w < 2 || in_h < 2) return MFSR_E_INVALID;
+    const int ow = in_w / 2, oh = in_h / 2;
+    dim3 b(32, 8), g(cdiv(ow, 32), cdiv(oh, 8));
+    pyramid_down_kernel<<<g, b, 0, (cudaStream_t)stream>>>(in, in_pitch, out, out_pitch, ow, oh);
+    MFSR_LAUNCH_CHECK();
+    return MFSR_OK;
+}
+
+extern "C" int mfsr_stage_fallback_upsample(const float* rgb, int64_t rgb_pitch, int width, int height,
+                                            float* out, int64_t out_pitch, const mfsr_merge_geom* geom, void* stream)
+{
+    if (!rgb || !out || !geom || geom->scale < 1) return MFSR_E_INVALID;
+    dim3 b(32, 8), g(cdiv(geom->out_w, 32), cdiv(geom->out_h, 8));
+    fallback_upsample_kernel<<<g, b, 0, (cudaStream_t)stream>>>(rgb, rgb_pitch, width, height, out, out_pitch, *geom);
+    MFSR_LAUNCH_CHECK();
+    return MFSR_OK;
+}

@@ -1,0 +1,37 @@
+// internal.h — private (non-ABI) launchers shared between translation units.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace mfsr {
+
+constexpr int CONS_MAX_M = 64, CONS_MAX_N = 32;
+struct PairTable { int8_t from[CONS_MAX_M], to[CONS_MAX_M]; };
+
+// Batched tile matcher: pair k matches image pt.from[k] (template) against pt.to[k], images of one
+// pyramid level stored as a stack (frame f at img + f*frame_stride).  Per-pair strides in BYTES.
+struct TileAlignBatch {
+    const uint8_t* img; int64_t pitch, frame_stride; int w, h;
+    const float2* pre; int64_t pre_pitch, pre_pair_stride;          // may be null
+    float2* out; int64_t out_pitch, out_pair_stride;
+    int2* argmin; int64_t argmin_pair_stride;                        // may be null (dense [ty][tx] per pair)
+    float* ssd; int64_t ssd_pair_stride;                             // may be null
+    PairTable pt; int n_pairs;
+    int T, M, tx, ty;
+    float bsx, bsy, rot, threshold;
+};
+int launch_tile_align(const TileAlignBatch& b, cudaStream_t st);
+
+struct UpsampleBatch {
+    const float2* in; int64_t in_pitch, in_pair_stride;
+    float2* out; int64_t out_pitch, out_pair_stride;
+    int n_pairs, oldLevel, newLevel, oldCX, oldCY, newCX, newCY, oldT, newT;
+};
+int launch_upsample_shifts(const UpsampleBatch& b, cudaStream_t st);
+
+// measured element (tile t, pair k) at measured[t*tile_stride + k*pair_stride] (in float2 units)
+int launch_consolidate(const float2* measured, int64_t tile_stride, int64_t pair_stride, const PairTable& pt, int m,
+                       int imageCount, int nTiles, int referenceImage, float2* one_to_one, float2* frame_shift,
+                       int* status, cudaStream_t st);
+
+}  // namespace mfsr

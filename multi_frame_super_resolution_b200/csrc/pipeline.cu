@@ -1,0 +1,465 @@
+// pipeline.cu — one-burst pipeline handle (SURVEY §3.2 A..I) and the misc C-ABI entry points.
+//
+// Mirrors the way finalProject/Project/multi_frame_sr.cpp:165-194 drives cv::superres
+// (create -> configure -> give it the frames -> pull the result), with the reference's
+// implicit conventions made explicit: one handle per GPU, an owned stream, one workspace
+// allocation, status codes instead of silent failure.
+#include "common.cuh"
+#include "internal.h"
+#include <new>
+#include <string.h>
+#include <vector>
+
+using namespace mfsr;
+
+namespace {
+
+enum Stage { ST_UPLOAD, ST_FRONTEND, ST_ALIGN, ST_CONSOLIDATE, ST_FLOW, ST_KERNEL, ST_ROBUST, ST_FALLBACK, ST_MERGE, ST_DOWNLOAD, ST_COUNT };
+const char* kStageNames[ST_COUNT] = {"upload", "frontend", "align", "consolidate", "flow", "kernel_params", "robustness", "fallback", "merge", "download"};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Level { int w, h, tx, ty; int64_t pitch, frame_stride; uint8_t* img; float2* shift; float2* pre; };
+
+}  // namespace
+
+struct mfsr_context {
+    mfsr_params p;
+    int device, max_w, max_h, max_frames;
+    cudaStream_t stream;
+    cudaEvent_t ev[ST_COUNT + 1];
+    float stage_ms[ST_COUNT];
+    bool timed;
+    // workspace
+    char* ws; size_t ws_bytes;
+    // burst state
+    int n, w, h, ref_idx, format; bool have_frames, ran;
+    int launches;
+    // buffers (all inside ws)
+    uint16_t* raw; int64_t raw_pitch, raw_fs;
+    float* rgb_half; int64_t rgbh_pitch, rgbh_fs;
+    float* gray; int64_t gray_pitch, gray_fs;
+    float* rgb_ref; int64_t rgb_pitch;
+    float2* flowA; float2* flowB; int64_t flow_pitch, flow_fs;
+    float4* mask; float4* mask_tmp; int64_t mask_pitch, mask_fs;
+    float4* kern; int64_t kern_pitch;
+    float* fallback; float* outbuf; int64_t out_pitch_own;
+    std::vector<Level> lv;
+    PairTable pt; int m;
+    int2* argmin; float2* one_to_one; float2* frame_shift; int* cons_status;
+    float2* flow_final;   // which of flowA/flowB holds the final flow
+    mfsr_merge_geom geom;
+};
+
+static void make_geom(const mfsr_params& p, int w, int h, mfsr_merge_geom* g)
+{
+    g->raw_w = w; g->raw_h = h; g->scale = p.scale;
+    if (p.full_frame) {
+        g->out_w = w * p.scale; g->out_h = h * p.scale; g->org_x = 0; g->org_y = 0;
+        g->clamp_x0 = 0; g->clamp_x1 = w - 1; g->clamp_y0 = 0; g->clamp_y1 = h - 1;
+    } else {
+        // generalisation of DeBayerKernels.cu:398-423 (s = 2: org = dim/2, clamp = [dim/4, dim/4 + dim/2 - 1])
+        const int s = p.scale;
+        g->out_w = w; g->out_h = h;
+        g->org_x = w * (s - 1) / 2; g->org_y = h * (s - 1) / 2;
+        g->clamp_x0 = g->org_x / s; g->clamp_x1 = g->clamp_x0 + w / s - 1;
+        g->clamp_y0 = g->org_y / s; g->clamp_y1 = g->clamp_y0 + h / s - 1;
+    }
+}
+
+extern "C" int mfsr_abi_version(void) { return MFSR_ABI_VERSION; }
+
+extern "C" const char* mfsr_error_string(int status)
+{
+    switch (status) {
+        case MFSR_OK: return "ok";
+        case MFSR_E_INVALID: return "invalid argument or unsupported configuration";
+        case MFSR_E_STATE: return "call order violated";
+        case MFSR_E_NOMEM: return "out of memory";
+        case MFSR_E_NODEVICE: return "no compute-capability-10.x CUDA device";
+        default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown mfsr status";
+    }
+}
+
+extern "C" int mfsr_default_params(mfsr_params* p)
+{
+    if (!p) return MFSR_E_INVALID;
+    memset(p, 0, sizeof(*p));
+    p->abi_version = MFSR_ABI_VERSION;
+    p->scale = 2; p->full_frame = 1;
+    p->cfa[0] = MFSR_RED; p->cfa[1] = MFSR_GREEN; p->cfa[2] = MFSR_GREEN; p->cfa[3] = MFSR_BLUE;
+    for (int c = 0; c < 3; c++) { p->black_level[c] = 64.0f; p->white_level[c] = 1023.0f - 64.0f; }
+    p->tile_size = 16; p->max_shift = 4; p->levels = 4; p->pair_span = 2; p->track_bits = 7; p->track_sigma = 0.5f;
+    p->min_threshold = 0.0f;
+    p->lk_iterations = 3; p->lk_half_window = 3; p->lk_min_det = 1e-3f;
+    p->Dth = 0.005f; p->Dtr = 0.012f; p->kDetail = 0.3f; p->kDenoise = 4.0f; p->kStretch = 4.0f; p->kShrink = 2.0f;
+    p->tensor_box_radius = 2;
+    p->alpha = 1e-3f; p->beta = 1e-5f; p->thresholdM = 0.8f; p->mask_erode_radius = 2;
+    p->weight_threshold = 0.1f; p->merge_flags = 0;
+    return MFSR_OK;
+}
+
+extern "C" int mfsr_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; d++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+static int validate_params(const mfsr_params* p)
+{
+    if (!p || p->abi_version != MFSR_ABI_VERSION) return MFSR_E_INVALID;
+    if (p->scale < 1 || p->scale > 4) return MFSR_E_INVALID;
+    if (p->tile_size < 4 || (p->tile_size & 3) || p->max_shift < 1 || p->levels < 1 || p->levels > 8) return MFSR_E_INVALID;
+    if (p->pair_span < 1 || p->track_bits < 1 || p->track_bits > 8) return MFSR_E_INVALID;
+    // exactness contract of the integer SSD (align.cu): 2 * T^2 * qmax^2 < 2^24
+    const int64_t qmax = (1 << p->track_bits) - 1;
+    if (2 * (int64_t)p->tile_size * p->tile_size * qmax * qmax >= (1ll << 24)) return MFSR_E_INVALID;
+    if (p->lk_iterations < 0 || p->lk_half_window < 1 || p->lk_half_window > 4) return MFSR_E_INVALID;
+    if (p->tensor_box_radius < 0 || p->tensor_box_radius > 3 || p->mask_erode_radius < 0 || p->mask_erode_radius > 8) return MFSR_E_INVALID;
+    for (int i = 0; i < 4; i++) if (p->cfa[i] < 0 || p->cfa[i] > 2) return MFSR_E_INVALID;
+    return MFSR_OK;
+}
+
+// carve the workspace; returns required bytes. If base == nullptr only measures.
+static size_t carve(mfsr_context* c, char* base, int n, int w, int h)
+{
+    size_t off = 0;
+    auto take = [&](size_t bytes) -> char* { char* p = base ? base + off : nullptr; off += align_up(bytes, 256); return p; };
+    const mfsr_params& p = c->p;
+    const int hw = w / 2, hh = h / 2;
+    c->raw_pitch = align_up((size_t)w * 2, 16); c->raw_fs = c->raw_pitch * h;
+    c->raw = (uint16_t*)take((size_t)c->raw_fs * n);
+    c->rgbh_pitch = (int64_t)hw * 12; c->rgbh_fs = c->rgbh_pitch * hh;
+    c->rgb_half = (float*)take((size_t)c->rgbh_fs * n);
+    c->gray_pitch = align_up((size_t)w * 4, 16); c->gray_fs = c->gray_pitch * h;
+    c->gray = (float*)take((size_t)c->gray_fs * n);
+    c->rgb_pitch = (int64_t)w * 12;
+    c->rgb_ref = (float*)take((size_t)c->rgb_pitch * h);
+    c->flow_pitch = align_up((size_t)w * 8, 16); c->flow_fs = c->flow_pitch * h;
+    c->flowA = (float2*)take((size_t)c->flow_fs * n);
+    c->flowB = (float2*)take((size_t)c->flow_fs * n);
+    c->mask_pitch = (int64_t)hw * 16; c->mask_fs = c->mask_pitch * hh;
+    c->mask = (float4*)take((size_t)c->mask_fs * n);
+    c->mask_tmp = (float4*)take((size_t)c->mask_fs);
+    c->kern_pitch = (int64_t)w * 16;
+    c->kern = (float4*)take((size_t)c->kern_pitch * h);
+    mfsr_merge_geom g; make_geom(p, w, h, &g);
+    c->out_pitch_own = (int64_t)g.out_w * 12;
+    c->fallback = (float*)take((size_t)c->out_pitch_own * g.out_h);
+    c->outbuf = (float*)take((size_t)c->out_pitch_own * g.out_h);
+    // measured pairs
+    int m = 0;
+    for (int i = 0; i < n; i++) for (int j = i + 1; j < n && j - i <= p.pair_span; j++) m++;
+    if (m < 1) m = 1;
+    // pyramid
+    c->lv.clear();
+    int lw = w, lh = h;
+    for (int l = 0; l < p.levels; l++) {
+        Level L; L.w = lw; L.h = lh;
+        L.tx = (lw - 2 * p.max_shift) / p.tile_size; L.ty = (lh - 2 * p.max_shift) / p.tile_size;
+        if (L.tx < 1 || L.ty < 1) break;
+        L.pitch = align_up((size_t)lw, 16); L.frame_stride = L.pitch * lh;
+        L.img = (uint8_t*)take((size_t)L.frame_stride * n);
+        L.shift = (float2*)take((size_t)L.tx * L.ty * 8 * m);
+        L.pre = (float2*)take((size_t)L.tx * L.ty * 8 * m);
+        c->lv.push_back(L);
+        lw /= 2; lh /= 2;
+    }
+    if (!c->lv.empty()) {
+        const size_t nt = (size_t)c->lv[0].tx * c->lv[0].ty;
+        c->argmin = (int2*)take(nt * 8 * m);
+        c->one_to_one = (float2*)take(nt * 8 * (n > 1 ? n - 1 : 1));
+        c->frame_shift = (float2*)take(nt * 8 * n);
+        c->cons_status = (int*)take(nt * 4);
+    }
+    return off;
+}
+
+extern "C" int mfsr_create(const mfsr_params* params, int device, int max_w, int max_h, int max_frames, mfsr_handle* out)
+{
+    if (!out) return MFSR_E_INVALID;
+    *out = nullptr;
+    int rc = validate_params(params);
+    if (rc) return rc;
+    if (max_w < 64 || max_h < 64 || (max_w & 1) || (max_h & 1) || max_frames < 1 || max_frames > CONS_MAX_N + 1) return MFSR_E_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return MFSR_E_NODEVICE; }
+    if (device < 0 || device >= ndev) return MFSR_E_INVALID;
+    int major = 0;
+    MFSR_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return MFSR_E_NODEVICE;      // the library is compiled for sm_100a only
+    MFSR_CUDA_TRY(cudaSetDevice(device));
+    mfsr_context* c = new (std::nothrow) mfsr_context();
+    if (!c) return MFSR_E_NOMEM;
+    c->p = *params; c->device = device; c->max_w = max_w; c->max_h = max_h; c->max_frames = max_frames;
+    c->have_frames = false; c->ran = false; c->timed = true; c->ws = nullptr; c->launches = 0;
+    c->ws_bytes = carve(c, nullptr, max_frames, max_w, max_h);
+    if (c->lv.empty()) { delete c; return MFSR_E_INVALID; }
+    cudaError_t e = cudaMalloc(&c->ws, c->ws_bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); delete c; return MFSR_E_NOMEM; }
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { cudaFree(c->ws); delete c; return (int)e; }
+    for (int i = 0; i <= ST_COUNT; i++) cudaEventCreate(&c->ev[i]);
+    memset(c->stage_ms, 0, sizeof(c->stage_ms));
+    *out = c;
+    return MFSR_OK;
+}
+
+extern "C" int mfsr_destroy(mfsr_handle h)
+{
+    if (!h) return MFSR_E_INVALID;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(h->ev[i]);
+    cudaStreamDestroy(h->stream);
+    cudaFree(h->ws);
+    delete h;
+    return MFSR_OK;
+}
+
+extern "C" int mfsr_output_size(mfsr_handle h, int width, int height, int* out_w, int* out_h)
+{
+    if (!h || !out_w || !out_h) return MFSR_E_INVALID;
+    mfsr_merge_geom g; make_geom(h->p, width, height, &g);
+    *out_w = g.out_w; *out_h = g.out_h;
+    return MFSR_OK;
+}
+
+extern "C" int64_t mfsr_workspace_bytes(mfsr_handle h) { return h ? (int64_t)h->ws_bytes : 0; }
+extern "C" void* mfsr_stream(mfsr_handle h) { return h ? (void*)h->stream : nullptr; }
+extern "C" int mfsr_synchronize(mfsr_handle h)
+{
+    if (!h) return MFSR_E_INVALID;
+    MFSR_CUDA_TRY(cudaSetDevice(h->device));
+    MFSR_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return MFSR_OK;
+}
+
+extern "C" int mfsr_set_frames(mfsr_handle h, const void* const* frames, int n, int width, int height, int64_t pitch,
+                               int format, int ref_idx, int on_host)
+{
+    if (!h || !frames || n < 1 || n > h->max_frames || width > h->max_w || height > h->max_h) return MFSR_E_INVALID;
+    if (width < 64 || height < 64 || (width & 1) || (height & 1) || ref_idx < 0 || ref_idx >= n || pitch < (int64_t)width * 2) return MFSR_E_INVALID;
+    if (format != MFSR_FMT_BAYER_U16 && format != MFSR_FMT_GRAY_U16) return MFSR_E_INVALID;
+    MFSR_CUDA_TRY(cudaSetDevice(h->device));
+    carve(h, h->ws, n, width, height);
+    if (h->lv.empty()) return MFSR_E_INVALID;
+    h->n = n; h->w = width; h->h = height; h->ref_idx = ref_idx; h->format = format;
+    make_geom(h->p, width, height, &h->geom);
+    // measured pairs (i, j), 0 < j - i <= pair_span
+    h->m = 0;
+    for (int i = 0; i < n; i++)
+        for (int j = i + 1; j < n && j - i <= h->p.pair_span; j++) {
+            if (h->m >= CONS_MAX_M) return MFSR_E_INVALID;
+            h->pt.from[h->m] = (int8_t)i; h->pt.to[h->m] = (int8_t)j; h->m++;
+        }
+    MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_UPLOAD], h->stream));
+    for (int f = 0; f < n; f++) {
+        if (!frames[f]) return MFSR_E_INVALID;
+        MFSR_CUDA_TRY(cudaMemcpy2DAsync((char*)h->raw + h->raw_fs * f, h->raw_pitch, frames[f], pitch, (size_t)width * 2, height,
+                                        on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+    }
+    h->have_frames = true; h->ran = false;
+    return MFSR_OK;
+}
+
+#define RUN(expr) do { int _rc = (expr); if (_rc) return _rc; h->launches++; } while (0)
+
+extern "C" int mfsr_run(mfsr_handle h, float* out, int64_t out_pitch, int out_on_host)
+{
+    if (!h || !out) return MFSR_E_INVALID;
+    if (!h->have_frames) return MFSR_E_STATE;
+    MFSR_CUDA_TRY(cudaSetDevice(h->device));
+    const mfsr_params& p = h->p;
+    cudaStream_t st = h->stream;
+    const int n = h->n, w = h->w, hh = h->h, hw2 = w / 2, hh2 = hh / 2;
+    h->launches = 0;
+    int cfa[4];
+    for (int i = 0; i < 4; i++) cfa[i] = (h->format == MFSR_FMT_GRAY_U16) ? MFSR_GREEN : p.cfa[i];
+    float scale[3];
+    for (int c = 0; c < 3; c++) scale[c] = 1.0f / p.white_level[c];
+
+    // ---- A. front end: half-res RGB, tracking gray (float + 7-bit), pyramid, demosaiced reference
+    MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_FRONTEND], st));
+    const float maxVal = p.white_level[1] + p.black_level[1];
+    for (int f = 0; f < n; f++) {
+        const uint16_t* raw = (const uint16_t*)((const char*)h->raw + h->raw_fs * f);
+        RUN(mfsr_stage_subsample3(raw, h->raw_pitch, (float*)((char*)h->rgb_half + h->rgbh_fs * f), h->rgbh_pitch, maxVal, hw2, hh2, cfa, st));
+        RUN(mfsr_stage_tracking_image(raw, h->raw_pitch, (float*)((char*)h->gray + h->gray_fs * f), h->gray_pitch,
+                                      h->lv[0].img + h->lv[0].frame_stride * f, h->lv[0].pitch, w, hh, cfa, p.black_level, scale,
+                                      p.track_sigma, p.track_bits, st));
+        for (size_t l = 1; l < h->lv.size(); l++)
+            RUN(mfsr_stage_pyramid_down(h->lv[l - 1].img + h->lv[l - 1].frame_stride * f, h->lv[l - 1].pitch, h->lv[l - 1].w, h->lv[l - 1].h,
+                                        h->lv[l].img + h->lv[l].frame_stride * f, h->lv[l].pitch, st));
+    }
+    RUN(mfsr_stage_demosaic((const uint16_t*)((const char*)h->raw + h->raw_fs * h->ref_idx), h->raw_pitch, h->rgb_ref, h->rgb_pitch,
+                            w, hh, cfa, p.black_level, scale, st));
+
+    // ---- C. pyramid tile matching, all measured pairs per launch, coarse -> fine
+    MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_ALIGN], st));
+    const int L = (int)h->lv.size();
+    if (n > 1) {
+        for (int l = L - 1; l >= 0; l--) {
+            Level& V = h->lv[l];
+            const int64_t grid_bytes = (int64_t)V.tx * V.ty * 8;
+            if (l < L - 1) {
+                Level& C = h->lv[l + 1];
+                UpsampleBatch u = {};
+                u.in = C.shift; u.in_pitch = (int64_t)C.tx * 8; u.in_pair_stride = (int64_t)C.tx * C.ty * 8;
+                u.out = V.pre; u.out_pitch = (int64_t)V.tx * 8; u.out_pair_stride = grid_bytes;
+                u.n_pairs = h->m; u.oldLevel = 1 << (l + 1); u.newLevel = 1 << l;
+                u.oldCX = C.tx; u.oldCY = C.ty; u.newCX = V.tx; u.newCY = V.ty; u.oldT = p.tile_size; u.newT = p.tile_size;
+                RUN(launch_upsample_shifts(u, st));
+            }
+            TileAlignBatch b = {};
+            b.img = V.img; b.pitch = V.pitch; b.frame_stride = V.frame_stride; b.w = V.w; b.h = V.h;
+            b.pre = (l < L - 1) ? V.pre : nullptr; b.pre_pitch = (int64_t)V.tx * 8; b.pre_pair_stride = grid_bytes;
+            b.out = V.shift; b.out_pitch = (int64_t)V.tx * 8; b.out_pair_stride = grid_bytes;
+            b.argmin = (l == 0) ? h->argmin : nullptr; b.argmin_pair_stride = grid_bytes;
+            b.ssd = nullptr; b.ssd_pair_stride = 0;
+            b.pt = h->pt; b.n_pairs = h->m; b.T = p.tile_size; b.M = p.max_shift; b.tx = V.tx; b.ty = V.ty;
+            // the global pre-alignment is expressed in full-resolution pixels
+            b.bsx = p.base_shift[0] / (float)(1 << l); b.bsy = p.base_shift[1] / (float)(1 << l); b.rot = p.base_rotation;
+            b.threshold = p.min_threshold;
+            RUN(launch_tile_align(b, st));
+        }
+    }
+    // ---- D. per-tile least squares -> reference->frame tile shifts
+    MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_CONSOLIDATE], st));
+    const int tx = h->lv[0].tx, ty = h->lv[0].ty, nt = tx * ty;
+    if (n > 1) {
+        RUN(launch_consolidate(h->lv[0].shift, 1, nt, h->pt, h->m, n, nt, h->ref_idx, h->one_to_one, h->frame_shift, h->cons_status, st));
+    } else {
+        MFSR_CUDA_TRY(cudaMemsetAsync(h->frame_shift, 0, (size_t)nt * 8, st));
+    }
+    // ---- E. dense flow + Lucas-Kanade refinement
+    MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_FLOW], st));
+    float2* cur = h->flowA; float2* nxt = h->flowB;
+    for (int f = 0; f < n; f++)
+        RUN(mfsr_stage_flow_from_tiles((const float*)(h->frame_shift + (size_t)f * nt), (int64_t)tx * 8, tx, ty, p.tile_size,
+                                       (float*)((char*)cur + h->flow_fs * f), h->flow_pitch, w, hh, p.base_shift[0], p.base_shift[1], p.base_rotation, st));
+    for (int it = 0; it < p.lk_iterations; it++) {
+        for (int f = 0; f < n; f++) {
+            if (f == h->ref_idx) {   // reference against itself: Iz == 0 -> UV == 0, flow unchanged
+                MFSR_CUDA_TRY(cudaMemcpyAsync((char*)nxt + h->flow_fs * f, (char*)cur + h->flow_fs * f, h->flow_fs, cudaMemcpyDeviceToDevice, st));
+                continue;
+            }
+            RUN(mfsr_stage_lk_iteration((const float*)((const char*)h->gray + h->gray_fs * h->ref_idx), (const float*)((const char*)h->gray + h->gray_fs * f),
+                                        h->gray_pitch, (const float*)((const char*)cur + h->flow_fs * f), (float*)((char*)nxt + h->flow_fs * f),
+                                        h->flow_pitch, w, hh, p.lk_half_window, p.lk_min_det, st));
+        }
+        float2* t = cur; cur = nxt; nxt = t;
+    }
+    h->flow_final = cur;
+    // ---- F. merge kernel parameters from the reference frame
+    MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_KERNEL], st));
+    RUN(mfsr_stage_kernel_params((const float*)((const char*)h->gray + h->gray_fs * h->ref_idx), h->gray_pitch, (float*)h->kern, h->kern_pitch,
+                                 w, hh, p.tensor_box_radius, p.Dth, p.Dtr, p.kDetail, p.kDenoise, p.kStretch, p.kShrink, st));
+    // ---- G. robustness masks
+    MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_ROBUST], st));
+    for (int f = 0; f < n; f++) {
+        RUN(mfsr_stage_robustness((const float*)((const char*)h->rgb_half + h->rgbh_fs * h->ref_idx), (const float*)((const char*)h->rgb_half + h->rgbh_fs * f),
+                                  h->rgbh_pitch, (const float*)((const char*)cur + h->flow_fs * f), h->flow_pitch,
+                                  (float*)((char*)h->mask + h->mask_fs * f), h->mask_pitch, (float*)h->mask_tmp, hw2, hh2,
+                                  p.alpha, p.beta, p.thresholdM, p.mask_erode_radius, st));
+        if (p.mask_erode_radius > 0) h->launches += 2;
+    }
+    // ---- fallback image (ApplyWeighting's inOutImg): demosaiced reference on the output grid
+    MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_FALLBACK], st));
+    RUN(mfsr_stage_fallback_upsample(h->rgb_ref, h->rgb_pitch, w, hh, h->fallback, h->out_pitch_own, &h->geom, st));
+    // ---- H+I. fused merge + normalise (+ gamma)
+    MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_MERGE], st));
+    float* dst = out_on_host ? h->outbuf : out;
+    const int64_t dst_pitch = out_on_host ? h->out_pitch_own : out_pitch;
+    RUN(mfsr_stage_merge(h->raw, h->raw_pitch, h->raw_fs, (const float*)h->mask, h->mask_pitch, h->mask_fs,
+                         (const float*)cur, h->flow_pitch, h->flow_fs, (const float*)h->kern, h->kern_pitch,
+                         h->fallback, h->out_pitch_own, dst, dst_pitch, nullptr, nullptr, 0, n, &h->geom, cfa,
+                         p.white_level, p.black_level, p.weight_threshold, p.merge_flags & ~MFSR_MERGE_NO_FALLBACK, st));
+    MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_DOWNLOAD], st));
+    if (out_on_host)
+        MFSR_CUDA_TRY(cudaMemcpy2DAsync(out, out_pitch, h->outbuf, h->out_pitch_own, (size_t)h->geom.out_w * 12, h->geom.out_h, cudaMemcpyDeviceToHost, st));
+    MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_COUNT], st));
+    h->ran = true;
+    if (out_on_host) MFSR_CUDA_TRY(cudaStreamSynchronize(st));
+    return MFSR_OK;
+}
+
+extern "C" int mfsr_get_stage_ms(mfsr_handle h, float* ms, int capacity)
+{
+    if (!h || !ms) return MFSR_E_INVALID;
+    if (!h->ran) return MFSR_E_STATE;
+    MFSR_CUDA_TRY(cudaSetDevice(h->device));
+    MFSR_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    int nwr = 0;
+    for (int i = 0; i < ST_COUNT && i < capacity; i++) {
+        float t = 0.f;
+        MFSR_CUDA_TRY(cudaEventElapsedTime(&t, h->ev[i], h->ev[i + 1]));
+        h->stage_ms[i] = t; ms[i] = t; nwr++;
+    }
+    return nwr;
+}
+
+extern "C" const char* mfsr_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : nullptr; }
+
+extern "C" int mfsr_get_tile_grid(mfsr_handle h, int* tilesX, int* tilesY, int* n_pairs)
+{
+    if (!h || !h->have_frames) return MFSR_E_STATE;
+    if (tilesX) *tilesX = h->lv[0].tx;
+    if (tilesY) *tilesY = h->lv[0].ty;
+    if (n_pairs) *n_pairs = h->n > 1 ? h->m : 0;
+    return MFSR_OK;
+}
+
+extern "C" int mfsr_get_tile_argmin(mfsr_handle h, int pair, int32_t* host_int2)
+{
+    if (!h || !host_int2) return MFSR_E_INVALID;
+    if (!h->ran || h->n < 2) return MFSR_E_STATE;
+    if (pair < 0 || pair >= h->m) return MFSR_E_INVALID;
+    MFSR_CUDA_TRY(cudaSetDevice(h->device));
+    const size_t nt = (size_t)h->lv[0].tx * h->lv[0].ty;
+    MFSR_CUDA_TRY(cudaMemcpyAsync(host_int2, h->argmin + nt * pair, nt * 8, cudaMemcpyDeviceToHost, h->stream));
+    MFSR_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return MFSR_OK;
+}
+
+extern "C" int mfsr_get_tile_shifts(mfsr_handle h, int frame, float* host_float2)
+{
+    if (!h || !host_float2) return MFSR_E_INVALID;
+    if (!h->ran) return MFSR_E_STATE;
+    if (frame < 0 || frame >= h->n) return MFSR_E_INVALID;
+    MFSR_CUDA_TRY(cudaSetDevice(h->device));
+    const size_t nt = (size_t)h->lv[0].tx * h->lv[0].ty;
+    MFSR_CUDA_TRY(cudaMemcpyAsync(host_float2, h->frame_shift + nt * frame, nt * 8, cudaMemcpyDeviceToHost, h->stream));
+    MFSR_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return MFSR_OK;
+}
+
+extern "C" int mfsr_get_buffer(mfsr_handle h, const char* name, void** dev_ptr, int64_t* pitch, int64_t* frame_stride)
+{
+    if (!h || !name || !dev_ptr) return MFSR_E_INVALID;
+    if (!h->have_frames) return MFSR_E_STATE;
+    int64_t pi = 0, fs = 0; void* p = nullptr;
+    if (!strcmp(name, "raw")) { p = h->raw; pi = h->raw_pitch; fs = h->raw_fs; }
+    else if (!strcmp(name, "rgb_half")) { p = h->rgb_half; pi = h->rgbh_pitch; fs = h->rgbh_fs; }
+    else if (!strcmp(name, "gray")) { p = h->gray; pi = h->gray_pitch; fs = h->gray_fs; }
+    else if (!strcmp(name, "gray_q0")) { p = h->lv[0].img; pi = h->lv[0].pitch; fs = h->lv[0].frame_stride; }
+    else if (!strcmp(name, "rgb_ref")) { p = h->rgb_ref; pi = h->rgb_pitch; fs = 0; }
+    else if (!strcmp(name, "flow")) { if (!h->ran) return MFSR_E_STATE; p = h->flow_final; pi = h->flow_pitch; fs = h->flow_fs; }
+    else if (!strcmp(name, "mask")) { p = h->mask; pi = h->mask_pitch; fs = h->mask_fs; }
+    else if (!strcmp(name, "kernel")) { p = h->kern; pi = h->kern_pitch; fs = 0; }
+    else if (!strcmp(name, "fallback")) { p = h->fallback; pi = h->out_pitch_own; fs = 0; }
+    else if (!strcmp(name, "tile_shift0")) { p = h->lv[0].shift; pi = (int64_t)h->lv[0].tx * 8; fs = (int64_t)h->lv[0].tx * h->lv[0].ty * 8; }
+    else return MFSR_E_INVALID;
+    *dev_ptr = p;
+    if (pitch) *pitch = pi;
+    if (frame_stride) *frame_stride = fs;
+    return MFSR_OK;
+}
+
+extern "C" int mfsr_last_launch_count(mfsr_handle h) { return h ? h->launches : 0; }

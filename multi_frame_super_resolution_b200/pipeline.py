@@ -1,0 +1,189 @@
+"""Host-side mirror of the reference's pull-style burst API over the C ABI.
+
+The reference's only runnable burst program drives `cv::superres::SuperResolution`
+(finalProject/Project/multi_frame_sr.cpp:165-194): create, setScale / setIterations /
+setInput, then pull the result with nextFrame().  `BurstSuperResolution` keeps that shape
+(set_scale, set_iterations, set_input, next_frame) on top of mfsr_create / mfsr_set_frames /
+mfsr_run.  All arithmetic happens in libmfsr_b200.so; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Params, check
+
+FMT_BAYER_U16 = 0
+FMT_GRAY_U16 = 1
+
+_cudart = None
+
+
+def _rt():
+    global _cudart
+    if _cudart is None:
+        for name in ("libcudart.so.12", "libcudart.so"):
+            try:
+                _cudart = C.CDLL(name)
+                break
+            except OSError:
+                continue
+        if _cudart is None:
+            raise ImportError("libcudart not found")
+        _cudart.cudaMemcpy2D.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]
+        _cudart.cudaMemcpy2D.restype = C.c_int
+    return _cudart
+
+
+def default_params() -> Params:
+    p = Params()
+    check(_lib.load().mfsr_default_params(C.byref(p)), "mfsr_default_params")
+    return p
+
+
+def measured_pairs(n_frames: int, pair_span: int):
+    """The (from, to) frame pairs the aligner measures: 0 < to - from <= pair_span."""
+    return [(i, j) for i in range(n_frames) for j in range(i + 1, min(n_frames, i + pair_span + 1))]
+
+
+class BurstSuperResolution:
+    """One handle = one GPU, one stream, one workspace (re-usable for many bursts)."""
+
+    def __init__(self, params: Optional[Params] = None, device: int = 0, max_width: int = 4032, max_height: int = 3024,
+                 max_frames: int = 8):
+        self._lib = _lib.load()
+        self.params = params if params is not None else default_params()
+        self.device = device
+        self._max = (max_width, max_height, max_frames)
+        self._h = C.c_void_p()
+        self._shape = None
+        self._n = 0
+        self._keep = None
+
+    # -- cv::superres-style setters (multi_frame_sr.cpp:179-182); take effect at the next (re)create
+    def set_scale(self, scale: int):
+        self._destroy()
+        self.params.scale = int(scale)
+
+    def set_iterations(self, iterations: int):
+        """Reference: BTV-L1 iterations; here: Lucas-Kanade refinement sweeps."""
+        self._destroy()
+        self.params.lk_iterations = int(iterations)
+
+    def _ensure(self):
+        if not self._h:
+            h = C.c_void_p()
+            check(self._lib.mfsr_create(C.byref(self.params), self.device, *self._max, C.byref(h)), "mfsr_create")
+            self._h = h
+
+    def _destroy(self):
+        if self._h:
+            self._lib.mfsr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def close(self):
+        self._destroy()
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    @property
+    def workspace_bytes(self) -> int:
+        self._ensure()
+        return int(self._lib.mfsr_workspace_bytes(self._h))
+
+    @property
+    def stream(self) -> int:
+        self._ensure()
+        return int(self._lib.mfsr_stream(self._h) or 0)
+
+    def output_size(self, width: int, height: int):
+        self._ensure()
+        ow, oh = C.c_int(), C.c_int()
+        check(self._lib.mfsr_output_size(self._h, width, height, C.byref(ow), C.byref(oh)), "mfsr_output_size")
+        return ow.value, oh.value
+
+    # -- setInput: frames is a CUDA tensor [N,H,W] (uint16/int16) or a host numpy/pinned tensor of the same shape
+    def set_input(self, frames, ref_idx: int = 0, fmt: int = FMT_BAYER_U16):
+        self._ensure()
+        if isinstance(frames, np.ndarray):
+            if frames.dtype != np.uint16 or frames.ndim != 3 or not frames.flags.c_contiguous:
+                raise ValueError("host frames must be a C-contiguous uint16 array [N,H,W]")
+            n, h, w = frames.shape
+            base, on_host = frames.ctypes.data, 1
+        else:
+            if frames.dim() != 3 or frames.element_size() != 2 or not frames.is_contiguous():
+                raise ValueError("frames must be a contiguous 16-bit tensor [N,H,W]")
+            n, h, w = frames.shape
+            base, on_host = frames.data_ptr(), 0 if frames.is_cuda else 1
+        ptrs = (C.c_void_p * n)(*[base + i * h * w * 2 for i in range(n)])
+        check(self._lib.mfsr_set_frames(self._h, ptrs, n, w, h, w * 2, fmt, ref_idx, on_host), "mfsr_set_frames")
+        self._shape = (h, w)
+        self._n = n
+        self._keep = frames          # the async H2D copies read it until the stream reaches them
+
+    # -- nextFrame: run the whole chain, return the float3 image
+    def next_frame(self, out=None, host: bool = False):
+        if self._shape is None:
+            raise RuntimeError("set_input() first")
+        ow, oh = self.output_size(self._shape[1], self._shape[0])
+        if host:
+            if out is None:
+                out = torch.empty((oh, ow, 3), dtype=torch.float32, pin_memory=True)
+            ptr = out.data_ptr() if isinstance(out, torch.Tensor) else out.ctypes.data
+            check(self._lib.mfsr_run(self._h, C.c_void_p(ptr), ow * 12, 1), "mfsr_run")
+            return out
+        if out is None:
+            out = torch.empty((oh, ow, 3), dtype=torch.float32, device=f"cuda:{self.device}")
+        check(self._lib.mfsr_run(self._h, C.c_void_p(out.data_ptr()), ow * 12, 0), "mfsr_run")
+        return out
+
+    def synchronize(self):
+        check(self._lib.mfsr_synchronize(self._h), "mfsr_synchronize")
+
+    # -- introspection used by tests / bench
+    def stage_ms(self) -> dict:
+        buf = (C.c_float * 16)()
+        n = self._lib.mfsr_get_stage_ms(self._h, buf, 16)
+        if n < 0:
+            check(n, "mfsr_get_stage_ms")
+        return {self._lib.mfsr_stage_name(i).decode(): float(buf[i]) for i in range(n)}
+
+    def launch_count(self) -> int:
+        return int(self._lib.mfsr_last_launch_count(self._h))
+
+    def tile_grid(self):
+        tx, ty, m = C.c_int(), C.c_int(), C.c_int()
+        check(self._lib.mfsr_get_tile_grid(self._h, C.byref(tx), C.byref(ty), C.byref(m)), "mfsr_get_tile_grid")
+        return tx.value, ty.value, m.value
+
+    def tile_argmin(self, pair: int) -> np.ndarray:
+        tx, ty, _ = self.tile_grid()
+        a = np.empty((ty, tx, 2), dtype=np.int32)
+        check(self._lib.mfsr_get_tile_argmin(self._h, pair, C.c_void_p(a.ctypes.data)), "mfsr_get_tile_argmin")
+        return a
+
+    def tile_shifts(self, frame: int) -> np.ndarray:
+        tx, ty, _ = self.tile_grid()
+        a = np.empty((ty, tx, 2), dtype=np.float32)
+        check(self._lib.mfsr_get_tile_shifts(self._h, frame, C.c_void_p(a.ctypes.data)), "mfsr_get_tile_shifts")
+        return a
+
+    def buffer(self, name: str, rows: int, row_bytes: int, frame: int = 0) -> np.ndarray:
+        """Copy an intermediate buffer of the last run to the host as raw bytes [rows, row_bytes]."""
+        ptr, pitch, fs = C.c_void_p(), C.c_int64(), C.c_int64()
+        check(self._lib.mfsr_get_buffer(self._h, name.encode(), C.byref(ptr), C.byref(pitch), C.byref(fs)), "mfsr_get_buffer")
+        self.synchronize()
+        out = np.empty((rows, row_bytes), dtype=np.uint8)
+        rc = _rt().cudaMemcpy2D(C.c_void_p(out.ctypes.data), row_bytes, C.c_void_p(ptr.value + fs.value * frame), pitch.value,
+                                row_bytes, rows, 2)
+        if rc != 0:
+            raise _lib.MfsrError(rc, "cudaMemcpy2D", "copy of intermediate buffer failed")
+        return out

@@ -1,0 +1,923 @@
+/*
+ * mfsr_oracle.c — CPU restatement of the reference burst-SR hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see mfsr_oracle.h).  Build: oracle/Makefile
+ *   gcc -O2 -ffp-contract=off -fno-fast-math -fopenmp -shared -fPIC
+ *
+ * What it follows (all under /root/reference/test_opencv/):
+ *   DeBayerKernels.cu:55-283 (demosaic/subsample), :290-468 (merge)
+ *   kernel.cu:119-259 (SSD), :265-378 (tiling), :503-636 (minimum),
+ *   :642-688 (upsample), :691-790 (kernel params), :426-481 (normalise),
+ *   :380-422 (gamma); ShiftMinimizerKernels.cu:81-218; opticalFlow.cu:28-325;
+ *   RobustnessModell.cu:29-157; tap generator main.cpp:370-391.
+ *
+ * PINNING.  The reference has no tests, golden vectors or fixtures for this
+ * path and its host driver is absent.  The oracle is pinned
+ * against the reference's OWN kernels compiled unmodified for sm_100a
+ * (oracle/ref_driver.cu -> oracle/_ref/libmfsr_ref.so) run on a B200 through
+ * gpurun on seeded inputs; the outputs of that run are frozen under
+ * tests/golden/ref_*.npz by tests/golden/make_ref_golden.py and checked by
+ * tests/test_oracle_golden.py.  Parts of the chain that exist only in the
+ * absent upstream host (tracking image, pyramid, tensor smoothing, mask
+ * erosion, cuFFT/cuBLAS glue, launch schedule) are "restated host" decisions
+ * documented in DESIGN.md; for those parity is unpinned by construction.
+ *
+ * Texture model.  The reference samples flow / tile shifts / kernel params /
+ * images through cudaTextureObject_t with normalised coordinates; the absent
+ * host fixes filter=linear, address=clamp.  tex_*() below model the hardware
+ * as documented in the CUDA programming guide (texel centre at i+0.5, the
+ * interpolation fraction kept in 1.8 fixed point), rounding the fraction to
+ * the nearest 1/256.
+ */
+#include "mfsr_oracle.h"
+#include <math.h>
+#include <float.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+static inline int   clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+static inline int   mini(int a, int b) { return a < b ? a : b; }
+static inline int   maxi(int a, int b) { return a > b ? a : b; }
+
+int orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n; return 1;
+#endif
+}
+
+/* ---- texture model ------------------------------------------------------ */
+static inline float q8(float a) { return floorf(a * 256.0f + 0.5f) * (1.0f / 256.0f); }
+
+/* linear-filtered fetch of component c of an nc-channel image at unnormalised
+ * texel coordinate (u,v); clamp addressing. */
+static inline void tex_setup(float u, int n, int* i0, int* i1, float* a)
+{
+    float xb = u - 0.5f;
+    float f = floorf(xb);
+    *a = q8(xb - f);
+    int i = (int)f;
+    *i0 = clampi(i, 0, n - 1);
+    *i1 = clampi(i + 1, 0, n - 1);
+}
+static inline float tex_mix(float t00, float t10, float t01, float t11, float a, float b)
+{
+    float top = t00 * (1.0f - a) + t10 * a;
+    float bot = t01 * (1.0f - a) + t11 * a;
+    return top * (1.0f - b) + bot * b;
+}
+static inline float tex_lin(const float* img, int w, int h, int nc, int c, float u, float v)
+{
+    int i0, i1, j0, j1; float a, b;
+    tex_setup(u, w, &i0, &i1, &a);
+    tex_setup(v, h, &j0, &j1, &b);
+    return tex_mix(img[((size_t)j0 * w + i0) * nc + c], img[((size_t)j0 * w + i1) * nc + c],
+                   img[((size_t)j1 * w + i0) * nc + c], img[((size_t)j1 * w + i1) * nc + c], a, b);
+}
+/* normalised coordinate -> unnormalised, as the hardware does */
+static inline float unnorm(float xn, int n) { return xn * (float)n; }
+
+/* ---- DeBayerKernels.cu:244 deBayersSubSample3 --------------------------- */
+void orc_subsample3(const uint16_t* raw, float* rgb3, float maxVal, int dimX, int dimY, const int cfa[4])
+{
+    float factor = 1.0f / maxVal;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < dimY; y++)
+        for (int x = 0; x < dimX; x++) {
+            float px[3] = {0, 0, 0};
+            for (int ix = 0; ix < 2; ix++)
+                for (int iy = 0; iy < 2; iy++) {
+                    int col = cfa[iy * 2 + ix];
+                    float r = (float)raw[(size_t)(2 * y + iy) * dimX * 2 + (2 * x + ix)];
+                    if (col == 1) px[1] += r * factor * 0.5f;
+                    else if (col == 0) px[0] = r * factor;
+                    else if (col == 2) px[2] = r * factor;
+                }
+            float* o = rgb3 + ((size_t)y * dimX + x) * 3;
+            o[0] = px[0]; o[1] = px[1]; o[2] = px[2];
+        }
+}
+
+/* ---- DeBayerKernels.cu:55 deBayerGreenKernel ---------------------------- */
+#define RAWC(xx, yy, c) ((raw[(size_t)(yy) * w + (xx)] - black[c]) * scale[c])
+void orc_debayer_green(const float* raw, float* rgb3, int w, int h, const int cfa[4], const float black[3], const float scale[3])
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 2; y < h - 2; y++)
+        for (int x = 2; x < w - 2; x++) {
+            int col = cfa[(y % 2) * 2 + (x % 2)];
+            float g = 0;
+            if (col == 1) g = RAWC(x, y, 1);
+            else if (col == 0 || col == 2) {
+                float p = RAWC(x, y, col);
+                float xm2 = RAWC(x - 2, y, col), xm1 = RAWC(x - 1, y, 1), xp1 = RAWC(x + 1, y, 1), xp2 = RAWC(x + 2, y, col);
+                float ym2 = RAWC(x, y - 2, col), ym1 = RAWC(x, y - 1, 1), yp1 = RAWC(x, y + 1, 1), yp2 = RAWC(x, y + 2, col);
+                float gradX = 0.5f * fabsf(xp1 - xm1);
+                float gradY = 0.5f * fabsf(yp1 - ym1);
+                float lapX = 0.25f * fabsf(2.0f * p - xm2 - xp2);
+                float lapY = 0.25f * fabsf(2.0f * p - ym2 - yp2);
+                float ipX = 0.125f * (-xm2 + 4.0f * xm1 + 2.0f * p + 4.0f * xp1 - xp2);
+                float ipY = 0.125f * (-ym2 + 4.0f * ym1 + 2.0f * p + 4.0f * yp1 - yp2);
+                float wgt = (gradY + lapY) / (gradX + gradY + lapX + lapY + 0.000000001f);
+                g = wgt * ipX + (1.0f - wgt) * ipY;
+            }
+            rgb3[((size_t)y * w + x) * 3 + 1] = g;
+        }
+}
+
+/* ---- DeBayerKernels.cu:153 deBayerRedBlueKernel ------------------------- */
+#define GRN(xx, yy) (rgb3[((size_t)(yy) * w + (xx)) * 3 + 1])
+void orc_debayer_redblue(const float* raw, float* rgb3, int w, int h, const int cfa[4], const float black[3], const float scale[3])
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 2; y < h - 2; y++)
+        for (int x = 2; x < w - 2; x++) {
+            int col = cfa[(y % 2) * 2 + (x % 2)];
+            int row = cfa[(y % 2) * 2 + ((x + 1) % 2)];
+            float r = 0, b = 0, g = GRN(x, y);
+            if (col == 1) {
+                if (row == 0) {
+                    r = g + 0.5f * ((RAWC(x - 1, y, 0) - GRN(x - 1, y)) + (RAWC(x + 1, y, 0) - GRN(x + 1, y)));
+                    b = g + 0.5f * ((RAWC(x, y - 1, 2) - GRN(x, y - 1)) + (RAWC(x, y + 1, 2) - GRN(x, y + 1)));
+                } else {
+                    b = g + 0.5f * ((RAWC(x - 1, y, 2) - GRN(x - 1, y)) + (RAWC(x + 1, y, 2) - GRN(x + 1, y)));
+                    r = g + 0.5f * ((RAWC(x, y - 1, 0) - GRN(x, y - 1)) + (RAWC(x, y + 1, 0) - GRN(x, y + 1)));
+                }
+            } else if (col == 0) {
+                r = RAWC(x, y, 0);
+                b = g + 0.25f * ((RAWC(x - 1, y - 1, 2) - GRN(x - 1, y - 1)) + (RAWC(x + 1, y - 1, 2) - GRN(x + 1, y - 1)) +
+                                 (RAWC(x + 1, y + 1, 2) - GRN(x + 1, y + 1)) + (RAWC(x - 1, y + 1, 2) - GRN(x - 1, y + 1)));
+            } else if (col == 2) {
+                b = RAWC(x, y, 2);
+                r = g + 0.25f * ((RAWC(x - 1, y - 1, 0) - GRN(x - 1, y - 1)) + (RAWC(x + 1, y - 1, 0) - GRN(x + 1, y - 1)) +
+                                 (RAWC(x + 1, y + 1, 0) - GRN(x + 1, y + 1)) + (RAWC(x - 1, y + 1, 0) - GRN(x - 1, y + 1)));
+            }
+            rgb3[((size_t)y * w + x) * 3 + 0] = r;
+            rgb3[((size_t)y * w + x) * 3 + 2] = b;
+        }
+}
+#undef RAWC
+#undef GRN
+
+/* ---- main.cpp:370 gaussin_filter_1D ------------------------------------- */
+int orc_gauss_taps(float sigma, float* taps)
+{
+    if (sigma <= 0) { for (int i = 0; i < 9; i++) taps[i] = (i == 4) ? 1.0f : 0.0f; return 9; }
+    int size = (int)(sigma / 0.6f - 0.4f) * 2 + 1 + 2;
+    if (size > 99) size = 99;
+    int center = size / 2;
+    for (int i = 0; i < size; i++) { int x = i - center; taps[i] = (float)(exp(-(x * x) / (2 * sigma * sigma))); }
+    float sum = 0;
+    for (int i = 0; i < size; i++) sum += taps[i];
+    for (int i = 0; i < size; i++) taps[i] /= sum;
+    return size;
+}
+
+/* ---- restated host: tracking image -------------------------------------- */
+void orc_tracking_image(const float* rgb3, float* gray, uint8_t* gray_q, int w, int h, float sigma, int track_bits)
+{
+    float taps[99];
+    int nt = orc_gauss_taps(sigma, taps), c = nt / 2;
+    float* lum = (float*)malloc((size_t)w * h * sizeof(float));
+    float* tmp = (float*)malloc((size_t)w * h * sizeof(float));
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const float* p = rgb3 + ((size_t)y * w + x) * 3;
+            lum[(size_t)y * w + x] = 0.25f * p[0] + 0.5f * p[1] + 0.25f * p[2];
+        }
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            float acc = 0;
+            for (int k = 0; k < nt; k++) acc += taps[k] * lum[(size_t)y * w + clampi(x + k - c, 0, w - 1)];
+            tmp[(size_t)y * w + x] = acc;
+        }
+    float qmax = (float)((1 << track_bits) - 1);
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            float acc = 0;
+            for (int k = 0; k < nt; k++) acc += taps[k] * tmp[(size_t)clampi(y + k - c, 0, h - 1) * w + x];
+            if (gray) gray[(size_t)y * w + x] = acc;
+            if (gray_q) {
+                float q = floorf(acc * qmax + 0.5f);
+                q = fminf(fmaxf(q, 0.0f), qmax);
+                gray_q[(size_t)y * w + x] = (uint8_t)q;
+            }
+        }
+    free(lum); free(tmp);
+}
+
+void orc_pyramid_down(const uint8_t* in, int in_w, int in_h, uint8_t* out)
+{
+    int ow = in_w / 2, oh = in_h / 2;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < oh; y++)
+        for (int x = 0; x < ow; x++) {
+            int s = in[(size_t)(2 * y) * in_w + 2 * x] + in[(size_t)(2 * y) * in_w + 2 * x + 1] +
+                    in[(size_t)(2 * y + 1) * in_w + 2 * x] + in[(size_t)(2 * y + 1) * in_w + 2 * x + 1];
+            out[(size_t)y * ow + x] = (uint8_t)((s + 2) >> 2);
+        }
+}
+
+/* ---- kernel.cu:265 / :324 tile extraction ------------------------------- */
+static void tile_disp(int tix, int tiy, int T, int w, int h, float prex, float prey, float bsx, float bsy, float rot, int* dx, int* dy)
+{
+    float sf = sinf(rot), cf = cosf(rot);
+    float sx = prex, sy = prey;
+    sx += cf * -bsx - sf * -bsy;
+    sy += sf * -bsx + cf * -bsy;
+    float pcx = (float)(tix * T + T / 2 - w / 2);
+    float pcy = (float)(tiy * T + T / 2 - h / 2);
+    sx += cf * pcx - sf * pcy - pcx;
+    sy += sf * pcx + cf * pcy - pcy;
+    *dx = (int)roundf(sx); *dy = (int)roundf(sy);
+}
+void orc_tiles_border(const float* img, float* tiles, int w, int h, int M, int T, int tx, int ty, float bsx, float bsy, float rot)
+{
+    int P = T + 2 * M;
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < tx * ty; t++) {
+        int tiy = t / tx, tix = t - tiy * tx, dx, dy;
+        tile_disp(tix, tiy, T, w, h, 0.0f, 0.0f, bsx, bsy, rot, &dx, &dy);
+        for (int py = 0; py < P; py++)
+            for (int px = 0; px < P; px++) {
+                float v = 0;
+                if (!(px < M || py < M || px >= T + M || py >= T + M)) {
+                    int ix = (int)fminf(fmaxf((float)(tix * T + px + dx), 0), (float)(w - 1));
+                    int iy = (int)fminf(fmaxf((float)(tiy * T + py + dy), 0), (float)(h - 1));
+                    v = img[(size_t)iy * w + ix];
+                }
+                tiles[((size_t)t * P + py) * P + px] = v;
+            }
+    }
+}
+void orc_tiles_preshift(const float* img, float* tiles, const float* pre2, int w, int h, int M, int T, int tx, int ty, float bsx, float bsy, float rot)
+{
+    int P = T + 2 * M;
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < tx * ty; t++) {
+        int tiy = t / tx, tix = t - tiy * tx, dx, dy;
+        float prx = pre2 ? pre2[2 * t] : 0.0f, pry = pre2 ? pre2[2 * t + 1] : 0.0f;
+        tile_disp(tix, tiy, T, w, h, prx, pry, bsx, bsy, rot, &dx, &dy);
+        for (int py = 0; py < P; py++)
+            for (int px = 0; px < P; px++) {
+                int ix = (int)fminf(fmaxf((float)(tix * T + px + dx), 0), (float)(w - 1));
+                int iy = (int)fminf(fmaxf((float)(tiy * T + py + dy), 0), (float)(h - 1));
+                tiles[((size_t)t * P + py) * P + px] = img[(size_t)iy * w + ix];
+            }
+    }
+}
+
+/* Circular cross-correlation cc[s] = sum_p a[p] * b[(p+s) mod P]  (what
+ * IFFT(conj(FFT(a)) * FFT(b)) / P^2 equals; kernel.cu:485 + absent cuFFT host).
+ * Summed row-major over p.  Terms with a[p]==0 are skipped (x + 0*y == x). */
+void orc_cross_correlation(const float* a_tiles, const float* b_tiles, float* cc, int P, int tiles_n)
+{
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < tiles_n; t++) {
+        const float* a = a_tiles + (size_t)t * P * P;
+        const float* b = b_tiles + (size_t)t * P * P;
+        float* o = cc + (size_t)t * P * P;
+        for (int sy = 0; sy < P; sy++)
+            for (int sx = 0; sx < P; sx++) {
+                float acc = 0;
+                for (int py = 0; py < P; py++) {
+                    int by = py + sy; if (by >= P) by -= P;
+                    for (int px = 0; px < P; px++) {
+                        float av = a[py * P + px];
+                        if (av == 0.0f) continue;
+                        int bx = px + sx; if (bx >= P) bx -= P;
+                        acc += av * b[by * P + bx];
+                    }
+                }
+                o[sy * P + sx] = acc;
+            }
+    }
+}
+/* same, but only the (2M+1)^2 lags normalizedCC reads (for speed) */
+static void cross_correlation_lags(const float* a_tiles, const float* b_tiles, float* cc, int P, int M, int tiles_n)
+{
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < tiles_n; t++) {
+        const float* a = a_tiles + (size_t)t * P * P;
+        const float* b = b_tiles + (size_t)t * P * P;
+        float* o = cc + (size_t)t * P * P;
+        for (int ly = -M; ly <= M; ly++)
+            for (int lx = -M; lx <= M; lx++) {
+                int sy = ly < 0 ? P + ly : ly, sx = lx < 0 ? P + lx : lx;
+                float acc = 0;
+                for (int py = M; py < P - M; py++) {
+                    int by = py + sy; if (by >= P) by -= P;
+                    for (int px = M; px < P - M; px++) {
+                        int bx = px + sx; if (bx >= P) bx -= P;
+                        acc += a[py * P + px] * b[by * P + bx];
+                    }
+                }
+                o[sy * P + sx] = acc;
+            }
+    }
+}
+
+/* ---- kernel.cu:119 squaredSum ------------------------------------------- */
+void orc_squared_sum(const float* tiles, float* out, int M, int T, int tiles_n)
+{
+    int P = T + 2 * M;
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < tiles_n; t++) {
+        float sum = 0;
+        for (int y = 0; y < T; y++)
+            for (int x = 0; x < T; x++) {
+                float p = tiles[(size_t)t * P * P + (y + M) * P + x + M];
+                sum += p * p;
+            }
+        out[t] = sum;
+    }
+}
+/* ---- kernel.cu:149 boxFilterWithBorderX --------------------------------- */
+void orc_box_x(const float* in, float* out, int M, int T, int tiles_n)
+{
+    int P = T + 2 * M;
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < tiles_n; t++)
+        for (int y = 0; y < P; y++)
+            for (int x = 0; x < P; x++) {
+                float o = 0;
+                if (x >= T / 2 && x <= M * 2 + T / 2)
+                    for (int s = -T / 2; s < T / 2; s++) {
+                        float v = in[(size_t)t * P * P + y * P + x + s];
+                        o += v * v;
+                    }
+                out[(size_t)t * P * P + y * P + x] = o;
+            }
+}
+/* ---- kernel.cu:186 boxFilterWithBorderY --------------------------------- */
+void orc_box_y(const float* in, float* out, int M, int T, int tiles_n)
+{
+    int P = T + 2 * M;
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < tiles_n; t++)
+        for (int y = 0; y < P; y++)
+            for (int x = 0; x < P; x++) {
+                float o = 0;
+                if (y >= T / 2 && y <= M * 2 + T / 2)
+                    for (int s = -T / 2; s < T / 2; s++) o += in[(size_t)t * P * P + (y + s) * P + x];
+                out[(size_t)t * P * P + y * P + x] = o;
+            }
+}
+/* ---- kernel.cu:227 normalizedCC ----------------------------------------- */
+void orc_normalized_cc(const float* cc, const float* sq, const float* box, float* ssd, int M, int T, int tiles_n)
+{
+    int P = T + 2 * M, S = 2 * M + 1;
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < tiles_n; t++)
+        for (int py = 0; py <= 2 * M; py++)
+            for (int px = 0; px <= 2 * M; px++) {
+                int shx = px - M, shy = py - M, fx = shx, fy = shy;
+                if (fx < 0) fx = P + shx;
+                if (fy < 0) fy = P + shy;
+                size_t icc = (size_t)t * P * P + fy * P + fx;
+                size_t ibx = (size_t)t * P * P + (P / 2 + shy) * P + (P / 2 + shx);
+                ssd[(size_t)t * S * S + py * S + px] = sq[t] + box[ibx] - 2 * cc[icc];
+            }
+}
+/* ---- kernel.cu:503-636 findMinimum -------------------------------------- */
+static const float FA11[9] = {1.0f / 4.0f, -2.0f / 4.0f, 1.0f / 4.0f, 2.0f / 4.0f, -4.0f / 4.0f, 2.0f / 4.0f, 1.0f / 4.0f, -2.0f / 4.0f, 1.0f / 4.0f};
+static const float FA22[9] = {1.0f / 4.0f, 2.0f / 4.0f, 1.0f / 4.0f, -2.0f / 4.0f, -4.0f / 4.0f, -2.0f / 4.0f, 1.0f / 4.0f, 2.0f / 4.0f, 1.0f / 4.0f};
+static const float FA12[9] = {1.0f / 4.0f, 0.0f, -1.0f / 4.0f, 0.0f, 0.0f, 0.0f, -1.0f / 4.0f, 0.0f, 1.0f / 4.0f};
+static const float FB1[9] = {-1.0f / 8.0f, 0.0f, 1.0f / 8.0f, -2.0f / 8.0f, 0.0f, 2.0f / 8.0f, -1.0f / 8.0f, 0.0f, 1.0f / 8.0f};
+static const float FB2[9] = {-1.0f / 8.0f, -2.0f / 8.0f, -1.0f / 8.0f, 0.0f, 0.0f, 0.0f, 1.0f / 8.0f, 2.0f / 8.0f, 1.0f / 8.0f};
+
+void orc_find_minimum(const float* ssd, float* coord2, int32_t* argmin2, int M, int tiles_n, float threshold)
+{
+    int S = 2 * M + 1, n = S * S;
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < tiles_n; t++) {
+        const float* im = ssd + (size_t)t * n;
+        float minVal = FLT_MAX, maxVal = -FLT_MAX; int minIdx = -1;
+        for (int i = 0; i < n; i++) {
+            float v = im[i];
+            maxVal = fmaxf(maxVal, v);
+            if (v < minVal) { minVal = v; minIdx = i; }
+        }
+        float cy = (float)((int)minIdx / (int)S);
+        float cx = minIdx - cy * S;
+        if (argmin2) { argmin2[2 * t] = (int)cx - M; argmin2[2 * t + 1] = (int)cy - M; }
+        if (cx < 1 || cy < 1 || cx >= 2 * M || cy >= 2 * M) { cx = 0; cy = 0; }
+        else {
+            float A11 = 0, A22 = 0, A12 = 0, b1 = 0, b2 = 0;
+            for (int i = 0; i < 9; i++) {
+                int off = (i < 3) ? (i - 1 - S) : (i < 6 ? i - 4 : i - 7 + S);
+                float g = im[minIdx + off];
+                A11 += FA11[i] * g; A22 += FA22[i] * g; A12 += FA12[i] * g; b1 += FB1[i] * g; b2 += FB2[i] * g;
+            }
+            A11 = fmaxf(A11, 0.0f); A22 = fmaxf(A22, 0.0f);
+            float det = A11 * A22 - A12 * A12;
+            if (det < 0) { A12 = 0; det = A11 * A22; }
+            if (det != 0) {
+                float muX = (A22 * b1 - A12 * b2) / det;
+                float muY = (A11 * b2 - A12 * b1) / det;
+                if (fabsf(muX) > 1) muX = 0;
+                if (fabsf(muY) > 1) muY = 0;
+                cx -= muX; cy -= muY;
+            }
+            cx -= M; cy -= M;
+        }
+        if (threshold + minVal > maxVal) { cx = 0; cy = 0; }
+        coord2[2 * t] = cx; coord2[2 * t + 1] = cy;
+    }
+}
+
+void orc_tile_align(const uint8_t* ref, const uint8_t* mov, int w, int h, const float* pre2,
+                    float* out_shift2, int32_t* argmin2, float* ssd_out,
+                    int T, int M, int tx, int ty, float bsx, float bsy, float rot, float threshold)
+{
+    int P = T + 2 * M, S = 2 * M + 1, nt = tx * ty;
+    size_t npx = (size_t)w * h;
+    float* rf = (float*)malloc(npx * 4); float* mf = (float*)malloc(npx * 4);
+    for (size_t i = 0; i < npx; i++) { rf[i] = (float)ref[i]; mf[i] = (float)mov[i]; }
+    float* ta = (float*)malloc((size_t)nt * P * P * 4);
+    float* tb = (float*)malloc((size_t)nt * P * P * 4);
+    float* cc = (float*)calloc((size_t)nt * P * P, 4);
+    float* bx = (float*)malloc((size_t)nt * P * P * 4);
+    float* by = (float*)malloc((size_t)nt * P * P * 4);
+    float* sq = (float*)malloc((size_t)nt * 4);
+    float* ssd = ssd_out ? ssd_out : (float*)malloc((size_t)nt * S * S * 4);
+    float* coord = (float*)malloc((size_t)nt * 8);
+    orc_tiles_border(rf, ta, w, h, M, T, tx, ty, bsx, bsy, rot);
+    orc_tiles_preshift(mf, tb, pre2, w, h, M, T, tx, ty, bsx, bsy, rot);
+    cross_correlation_lags(ta, tb, cc, P, M, nt);
+    orc_squared_sum(ta, sq, M, T, nt);
+    orc_box_x(tb, bx, M, T, nt);
+    orc_box_y(bx, by, M, T, nt);
+    orc_normalized_cc(cc, sq, by, ssd, M, T, nt);
+    orc_find_minimum(ssd, coord, argmin2, M, nt, threshold);
+    for (int t = 0; t < nt; t++) {
+        int tiy = t / tx, tix = t - tiy * tx, dxm, dym, dxr, dyr;
+        tile_disp(tix, tiy, T, w, h, pre2 ? pre2[2 * t] : 0.0f, pre2 ? pre2[2 * t + 1] : 0.0f, bsx, bsy, rot, &dxm, &dym);
+        tile_disp(tix, tiy, T, w, h, 0.0f, 0.0f, bsx, bsy, rot, &dxr, &dyr);
+        out_shift2[2 * t] = coord[2 * t] + (float)(dxm - dxr);
+        out_shift2[2 * t + 1] = coord[2 * t + 1] + (float)(dym - dyr);
+    }
+    free(rf); free(mf); free(ta); free(tb); free(cc); free(bx); free(by); free(sq); free(coord);
+    if (!ssd_out) free(ssd);
+}
+
+/* ---- kernel.cu:642 UpSampleShifts --------------------------------------- */
+void orc_upsample_shifts(const float* in2, float* out2, int oldLevel, int newLevel, int oldCX, int oldCY,
+                         int newCX, int newCY, int oldT, int newT)
+{
+    float factor = (float)oldLevel * oldT / (float)(newLevel * newT);
+    for (int ny = 0; ny < newCY; ny++)
+        for (int nx = 0; nx < newCX; nx++) {
+            float oldX = nx / factor, oldY = ny / factor;
+            int xmin = (int)floorf(oldX), xmax = (int)ceilf(oldX), ymin = (int)floorf(oldY), ymax = (int)ceilf(oldY);
+            xmin = mini(xmin, oldCX - 1); xmax = mini(xmax, oldCX - 1);
+            ymin = mini(ymin, oldCY - 1); ymax = mini(ymax, oldCY - 1);
+            const float* mm = in2 + 2 * ((size_t)ymin * oldCX + xmin);
+            const float* Mm = in2 + 2 * ((size_t)ymin * oldCX + xmax);
+            const float* mM = in2 + 2 * ((size_t)ymax * oldCX + xmin);
+            const float* MM = in2 + 2 * ((size_t)ymax * oldCX + xmax);
+            float o[2];
+            for (int c = 0; c < 2; c++) {
+                float t1 = mm[c] + (Mm[c] - mm[c]) * (1.0f - (xmax - oldX));
+                float t2 = mM[c] + (MM[c] - mM[c]) * (1.0f - (xmax - oldX));
+                o[c] = t1 + (t2 - t1) * (1.0f - (ymax - oldY));
+                o[c] *= oldLevel / (float)newLevel;
+            }
+            out2[2 * ((size_t)ny * newCX + nx)] = o[0];
+            out2[2 * ((size_t)ny * newCX + nx) + 1] = o[1];
+        }
+}
+
+/* ---- ShiftMinimizerKernels.cu: per-tile LSQ with outlier removal --------
+ * A is m x n1 column-major (idx + col*m, :137); row k has ones in columns
+ * pair_from[k] .. pair_to[k]-1.  Each sweep is the absent host's batched
+ * AtA -> inverse -> inv*At -> x, A*x, then checkForOutliers (:81).  A singular
+ * AtA (inversionInfo != 0, :97) ends the loop with x = 0 (restated host). */
+static int invert_gj(float* a, float* inv, int n)
+{
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) inv[i * n + j] = (i == j) ? 1.0f : 0.0f;
+    for (int c = 0; c < n; c++) {
+        int piv = c; float best = fabsf(a[c * n + c]);
+        for (int r = c + 1; r < n; r++) if (fabsf(a[r * n + c]) > best) { best = fabsf(a[r * n + c]); piv = r; }
+        if (best < 1e-6f) return 1;
+        if (piv != c) for (int j = 0; j < n; j++) {
+            float t = a[c * n + j]; a[c * n + j] = a[piv * n + j]; a[piv * n + j] = t;
+            t = inv[c * n + j]; inv[c * n + j] = inv[piv * n + j]; inv[piv * n + j] = t;
+        }
+        float d = 1.0f / a[c * n + c];
+        for (int j = 0; j < n; j++) { a[c * n + j] *= d; inv[c * n + j] *= d; }
+        for (int r = 0; r < n; r++) if (r != c) {
+            float f = a[r * n + c];
+            if (f != 0.0f) for (int j = 0; j < n; j++) { a[r * n + j] -= f * a[c * n + j]; inv[r * n + j] -= f * inv[c * n + j]; }
+        }
+    }
+    return 0;
+}
+void orc_consolidate_shifts(const float* measured2, const int* pair_from, const int* pair_to, int m,
+                            int imageCount, int tilesX, int tilesY, int referenceImage,
+                            float* one_to_one2, float* frame_shift2, int32_t* status)
+{
+    int n1 = imageCount - 1, nt = tilesX * tilesY;
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < nt; t++) {
+        float* A = (float*)malloc((size_t)m * n1 * 4);
+        float* b = (float*)malloc((size_t)m * 8);
+        float* AtA = (float*)malloc((size_t)n1 * n1 * 4);
+        float* inv = (float*)malloc((size_t)n1 * n1 * 4);
+        float* x = (float*)calloc((size_t)n1 * 2, 4);
+        for (int k = 0; k < m; k++) {
+            for (int c = 0; c < n1; c++) A[k + c * m] = (c >= pair_from[k] && c < pair_to[k]) ? 1.0f : 0.0f;
+            b[2 * k] = measured2[2 * ((size_t)t * m + k)]; b[2 * k + 1] = measured2[2 * ((size_t)t * m + k) + 1];
+        }
+        int removed = 0, st = 0;
+        for (;;) {
+            for (int i = 0; i < n1; i++) for (int j = 0; j < n1; j++) {
+                float s = 0; for (int k = 0; k < m; k++) s += A[k + i * m] * A[k + j * m];
+                AtA[i * n1 + j] = s;
+            }
+            if (invert_gj(AtA, inv, n1)) { for (int i = 0; i < 2 * n1; i++) x[i] = 0; st = -1; break; }
+            /* Atb then x = inv * Atb */
+            for (int c = 0; c < 2; c++) {
+                float Atb[64];
+                for (int i = 0; i < n1; i++) { float s = 0; for (int k = 0; k < m; k++) s += A[k + i * m] * b[2 * k + c]; Atb[i] = s; }
+                for (int i = 0; i < n1; i++) { float s = 0; for (int j = 0; j < n1; j++) s += inv[i * n1 + j] * Atb[j]; x[2 * i + c] = s; }
+            }
+            float mx = 1; int idx = -1;
+            for (int k = 0; k < m; k++) {
+                float ox = 0, oy = 0;
+                for (int c = 0; c < n1; c++) { ox += A[k + c * m] * x[2 * c]; oy += A[k + c * m] * x[2 * c + 1]; }
+                float dx = b[2 * k] - ox, dy = b[2 * k + 1] - oy, d = dx * dx + dy * dy;
+                if (d > mx) { idx = k; mx = d; }
+            }
+            if (idx == -1) break;
+            b[2 * idx] = 0; b[2 * idx + 1] = 0;
+            for (int c = 0; c < n1; c++) A[idx + c * m] = 0;
+            removed++;
+        }
+        if (status) status[t] = st < 0 ? -1 : removed;
+        if (one_to_one2) for (int i = 0; i < 2 * n1; i++) one_to_one2[(size_t)t * n1 * 2 + i] = x[i];
+        /* getOptimalShifts (:179) for every frame */
+        for (int f = 0; f < imageCount; f++) {
+            float tsx = 0, tsy = 0;
+            if (referenceImage < f) for (int i = referenceImage; i < f; i++) { tsx += x[2 * i]; tsy += x[2 * i + 1]; }
+            else if (f < referenceImage) for (int i = f; i < referenceImage; i++) { tsx -= x[2 * i]; tsy -= x[2 * i + 1]; }
+            frame_shift2[2 * ((size_t)f * nt + t)] = tsx; frame_shift2[2 * ((size_t)f * nt + t) + 1] = tsy;
+        }
+        free(A); free(b); free(AtA); free(inv); free(x);
+    }
+}
+
+/* ---- opticalFlow.cu:48 CreateFlowFieldFromTiles ------------------------- */
+void orc_flow_from_tiles(const float* tile2, int tilesX, int tilesY, int T, float* flow2, int w, int h,
+                         float bsx, float bsy, float rot)
+{
+    (void)T;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            float sx = cosf(rot) * -bsx - sinf(rot) * -bsy;
+            float sy = sinf(rot) * -bsx + cosf(rot) * -bsy;
+            float pcx = (float)(x - w / 2), pcy = (float)(y - h / 2);
+            sx += cosf(rot) * pcx - sinf(rot) * pcy - pcx;
+            sy += sinf(rot) * pcx + cosf(rot) * pcy - pcy;
+            float u = unnorm((x + 0.5f) / (float)w, tilesX), v = unnorm((y + 0.5f) / (float)h, tilesY);
+            sx += tex_lin(tile2, tilesX, tilesY, 2, 0, u, v);
+            sy += tex_lin(tile2, tilesX, tilesY, 2, 1, u, v);
+            flow2[2 * ((size_t)y * w + x)] = sx; flow2[2 * ((size_t)y * w + x) + 1] = sy;
+        }
+}
+/* ---- opticalFlow.cu:28 WarpingKernel ------------------------------------ */
+void orc_warp(const float* flow2, const float* img, float* out, int w, int h)
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            float un = unnorm(((float)x + 0.5f) / (float)w, w), vn = unnorm(((float)y + 0.5f) / (float)h, h);
+            float shx = tex_lin(flow2, w, h, 2, 0, un, vn), shy = tex_lin(flow2, w, h, 2, 1, un, vn);
+            float u = unnorm(((float)x + 0.5f + shx) / (float)w, w);
+            float v = unnorm(((float)y + 0.5f + shy) / (float)h, h);
+            out[(size_t)y * w + x] = tex_lin(img, w, h, 1, 0, u, v);
+        }
+}
+/* ---- opticalFlow.cu:97 / :151 derivatives -------------------------------
+ * The fetches are at exact texel centres (x + k*dx): modelled as clamped reads. */
+static inline float rd(const float* im, int w, int h, int x, int y) { return im[(size_t)clampi(y, 0, h - 1) * w + clampi(x, 0, w - 1)]; }
+static inline float d5x(const float* im, int w, int h, int x, int y)
+{
+    float t = rd(im, w, h, x + 2, y); t -= rd(im, w, h, x + 1, y) * 8.0f; t += rd(im, w, h, x - 1, y) * 8.0f; t -= rd(im, w, h, x - 2, y); t /= 12.0f; return t;
+}
+static inline float d5y(const float* im, int w, int h, int x, int y)
+{
+    float t = rd(im, w, h, x, y + 2); t -= rd(im, w, h, x, y + 1) * 8.0f; t += rd(im, w, h, x, y - 1) * 8.0f; t -= rd(im, w, h, x, y - 2); t /= 12.0f; return t;
+}
+void orc_derivatives(const float* src, const float* tgt, float* Ix, float* Iy, float* Iz, int w, int h)
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            size_t i = (size_t)y * w + x;
+            Ix[i] = (d5x(src, w, h, x, y) + d5x(tgt, w, h, x, y)) * 0.5f;
+            Iz[i] = src[i] - tgt[i];
+            Iy[i] = (d5y(src, w, h, x, y) + d5y(tgt, w, h, x, y)) * 0.5f;
+        }
+}
+void orc_derivatives2(const float* img, float* Ix, float* Iy, int w, int h)
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            size_t i = (size_t)y * w + x;
+            Ix[i] = d5x(img, w, h, x, y); Iy[i] = d5y(img, w, h, x, y);
+        }
+}
+/* ---- opticalFlow.cu:190 lucasKanadeOptim -------------------------------- */
+void orc_lucas_kanade(float* flow2, const float* imFx, const float* imFy, const float* imFt, int w, int h, int hw, float minDet)
+{
+    int ws = hw * 2 + 1;
+#pragma omp parallel for schedule(static)
+    for (int py = hw; py < h - hw; py++)
+        for (int px = hw; px < w - hw; px++) {
+            float mm[4] = {0, 0, 0, 0}, inv[4], UT[4], S[4], V[4], UV[2];
+            for (int y = -hw; y <= hw; y++)
+                for (int x = -hw; x <= hw; x++) {
+                    float dx = imFx[(size_t)(py + y) * w + px + x], dy = imFy[(size_t)(py + y) * w + px + x];
+                    mm[0] += dx * dx; mm[1] += dx * dy; mm[3] += dy * dy;
+                }
+            mm[2] = mm[1];
+            float a = mm[0], b = mm[1], c = mm[2], d = mm[3];
+            float theta = 0.5f * atan2f(2.0f * a * c + 2.0f * b * d, a * a + b * b - c * c - d * d);
+            float ct = cosf(theta), st = sinf(theta);
+            UT[0] = ct; UT[2] = -st; UT[1] = st; UT[3] = ct;
+            float S1 = a * a + b * b + c * c + d * d;
+            float S2 = sqrtf((a * a + b * b - c * c - d * d) * (a * a + b * b - c * c - d * d) + 4 * (a * c + b * d) * (a * c + b * d));
+            float sigma1 = sqrtf((S1 + S2) / 2), sigma2 = sqrtf((S1 - S2) / 2);
+            float smin = fminf(sigma1, sigma1);           /* sic: opticalFlow.cu:255 */
+            if (smin < minDet) continue;
+            sigma1 = sigma1 != 0 ? 1.0f / sigma1 : 0;
+            sigma2 = sigma2 != 0 ? 1.0f / sigma2 : 0;
+            S[0] = sigma1; S[1] = 0; S[2] = 0; S[3] = sigma2;
+            float eps = 0.5f * atan2f(2.0f * a * b + 2.0f * c * d, a * a - b * b + c * c - d * d);
+            float ce = cosf(eps), se = sinf(eps);
+            float s11 = (a * ct + c * st) * ce + (b * ct + d * st) * se;
+            float s22 = (a * st - c * ct) * se + (-b * st + d * ct) * ce;
+            s11 = s11 > 0.0f ? 1.0f : s11 < 0 ? -1.0f : 0.0f;
+            s22 = s22 > 0.0f ? 1.0f : s22 < 0 ? -1.0f : 0.0f;
+            V[0] = s11 * ce; V[1] = -s22 * se; V[2] = s11 * se; V[3] = s22 * ce;
+            mm[0] = S[0] * UT[0] + S[1] * UT[2]; mm[1] = S[0] * UT[1] + S[1] * UT[3];
+            mm[2] = S[2] * UT[0] + S[3] * UT[2]; mm[3] = S[2] * UT[1] + S[3] * UT[3];
+            inv[0] = V[0] * mm[0] + V[1] * mm[2]; inv[1] = V[0] * mm[1] + V[1] * mm[3];
+            inv[2] = V[2] * mm[0] + V[3] * mm[2]; inv[3] = V[2] * mm[1] + V[3] * mm[3];
+            UV[0] = 0; UV[1] = 0;
+            for (int i = 0; i < ws * ws; i++) {
+                int y = i / ws, x = i - y * ws;
+                size_t g = (size_t)(py + y - hw) * w + px + x - hw;
+                float dx = imFx[g], dy = imFy[g], dt = imFt[g];
+                UV[0] += (inv[0] * dx + inv[1] * dy) * dt;
+                UV[1] += (inv[2] * dx + inv[3] * dy) * dt;
+            }
+            UV[0] = isnan(UV[0]) ? 0 : UV[0];
+            UV[1] = isnan(UV[1]) ? 0 : UV[1];
+            flow2[2 * ((size_t)py * w + px)] += UV[0];
+            flow2[2 * ((size_t)py * w + px) + 1] += UV[1];
+        }
+}
+void orc_lk_iteration(const float* ref, const float* mov, const float* flow_in2, float* flow_out2, int w, int h, int hw, float minDet)
+{
+    size_t n = (size_t)w * h;
+    float* warped = (float*)malloc(n * 4); float* Ix = (float*)malloc(n * 4); float* Iy = (float*)malloc(n * 4); float* Iz = (float*)malloc(n * 4);
+    if (flow_out2 != flow_in2) memcpy(flow_out2, flow_in2, n * 8);
+    orc_warp(flow_out2, mov, warped, w, h);
+    /* restated host: texSource = warped moved frame, texTarget = reference.  The reference's 5-tap
+     * stencil (opticalFlow.cu:116-120) is f(x+2) - 8 f(x+1) + 8 f(x-1) - f(x-2), i.e. MINUS the
+     * derivative, so only Iz = warped - ref makes `shift += UV` (:322) descend. */
+    orc_derivatives(warped, ref, Ix, Iy, Iz, w, h);
+    orc_lucas_kanade(flow_out2, Ix, Iy, Iz, w, h, hw, minDet);
+    free(warped); free(Ix); free(Iy); free(Iz);
+}
+
+/* ---- kernel.cu:691 ComputeStructureTensor ------------------------------- */
+void orc_structure_tensor(const float* Ix, const float* Iy, float* t3, int w, int h)
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            size_t i = (size_t)y * w + x; float dx = Ix[i], dy = Iy[i];
+            t3[3 * i] = dx * dx; t3[3 * i + 1] = dy * dy; t3[3 * i + 2] = dx * dy;
+        }
+}
+/* restated host: (2r+1)^2 box mean, clamp border, row-major sum then * 1/n */
+void orc_box_mean3(const float* in3, float* out3, int w, int h, int r)
+{
+    float inv = 1.0f / (float)((2 * r + 1) * (2 * r + 1));
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            for (int c = 0; c < 3; c++) {
+                float s = 0;
+                for (int dy = -r; dy <= r; dy++)
+                    for (int dx = -r; dx <= r; dx++)
+                        s += in3[3 * ((size_t)clampi(y + dy, 0, h - 1) * w + clampi(x + dx, 0, w - 1)) + c];
+                out3[3 * ((size_t)y * w + x) + c] = s * inv;
+            }
+}
+/* ---- kernel.cu:718 ComputeKernelParam ----------------------------------- */
+void orc_kernel_param(float* k3, int w, int h, float Dth, float Dtr, float kDetail, float kDenoise, float kStretch, float kShrink)
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            float* p = k3 + 3 * ((size_t)y * w + x);
+            float a11 = p[0], a22 = p[1], a12 = p[2];
+            float help = sqrtf((a22 - a11) * (a22 - a11) + 4.0f * a12 * a12);
+            float c = 2.0f * a12, s = a22 - a11 + help;
+            float norm = sqrtf(c * c + s * s);
+            if (norm > 0) { c /= norm; s /= norm; } else { c = 1; s = 0; }
+            float lam1 = (a11 + a22 + help) / 2.0f, lam2 = (a11 + a22 - help) / 2.0f;
+            float A = 1 + sqrtf((lam1 - lam2) * (lam1 - lam2) / ((lam1 + lam2) * (lam1 + lam2)));
+            float D = 1 - sqrtf(lam1) / Dtr + Dth;
+            D = fmaxf(fminf(1.0f, D), 0.0f);
+            float k1h = kDetail * kStretch * A, k2h = kDetail / kShrink * A;
+            float k1 = ((1.0f - D) * k1h + D * kDetail * kDenoise);
+            float k2 = ((1.0f - D) * k2h + D * kDetail * kDenoise);
+            k1 *= k1; k2 *= k2;
+            float x2 = c, y2 = s, x1 = s, y1 = -c;
+            float b11 = k1 * x1 * x1 + x2 * x2 * k2;
+            float b12 = k1 * x1 * y1 + x2 * y2 * k2;
+            float b22 = k1 * y1 * y1 + y2 * y2 * k2;
+            float det = b11 * b22 - b12 * b12 + 0.0000000001f;
+            p[0] = b22 / det; p[1] = b11 / det; p[2] = -b12 / det;
+        }
+}
+void orc_kernel_params(const float* gray, float* kernel4, int w, int h, int box_r, float Dth, float Dtr,
+                       float kDetail, float kDenoise, float kStretch, float kShrink)
+{
+    size_t n = (size_t)w * h;
+    float* Ix = (float*)malloc(n * 4); float* Iy = (float*)malloc(n * 4);
+    float* t3 = (float*)malloc(n * 12); float* s3 = (float*)malloc(n * 12);
+    orc_derivatives2(gray, Ix, Iy, w, h);
+    orc_structure_tensor(Ix, Iy, t3, w, h);
+    if (box_r > 0) orc_box_mean3(t3, s3, w, h, box_r); else memcpy(s3, t3, n * 12);
+    orc_kernel_param(s3, w, h, Dth, Dtr, kDetail, kDenoise, kStretch, kShrink);
+    for (size_t i = 0; i < n; i++) { kernel4[4 * i] = s3[3 * i]; kernel4[4 * i + 1] = s3[3 * i + 1]; kernel4[4 * i + 2] = s3[3 * i + 2]; kernel4[4 * i + 3] = 0; }
+    free(Ix); free(Iy); free(t3); free(s3);
+}
+
+/* ---- RobustnessModell.cu:29 ComputeRobustnessMask ----------------------- */
+void orc_robustness_mask(const float* ref3, const float* mov3, float* mask4, const float* flow2, int fw, int fh,
+                         int w, int h, float alpha, float beta, float thresholdM)
+{
+#pragma omp parallel for schedule(static)
+    for (int py = 1; py < h - 1; py++)
+        for (int px = 1; px < w - 1; px++) {
+            float meanRef[3] = {0, 0, 0}, meanMov[3] = {0, 0, 0}, stdRef[3] = {0, 0, 0}, pix[9][3];
+            float u = unnorm(((float)px + 0.5f) / (float)w, fw), v = unnorm(((float)py + 0.5f) / (float)h, fh);
+            float sfx = tex_lin(flow2, fw, fh, 2, 0, u, v), sfy = tex_lin(flow2, fw, fh, 2, 1, u, v);
+            float maxx = sfx, maxy = sfy, minx = sfx, miny = sfy;
+            for (int y = -2; y <= 2; y++)
+                for (int x = -2; x <= 2; x++) {
+                    float uu = unnorm(((float)px + x + 0.5f) / (float)w, fw), vv = unnorm(((float)py + y + 0.5f) / (float)h, fh);
+                    float sx = tex_lin(flow2, fw, fh, 2, 0, uu, vv), sy = tex_lin(flow2, fw, fh, 2, 1, uu, vv);
+                    maxx = fmaxf(sx, sfx); maxy = fmaxf(sy, sfy);      /* sic: :67-70 */
+                    minx = fminf(sx, sfx); miny = fminf(sy, sfy);
+                }
+            int shx = (int)roundf(sfx * 0.5f), shy = (int)roundf(sfy * 0.5f);
+            for (int y = -1; y <= 1; y++)
+                for (int x = -1; x <= 1; x++) {
+                    const float* p = ref3 + 3 * ((size_t)(py + y) * w + px + x);
+                    float* s = pix[(y + 1) * 3 + (x + 1)];
+                    s[0] = p[0]; s[1] = p[1]; s[2] = p[2];
+                    meanRef[0] += p[0]; meanRef[1] += p[1]; meanRef[2] += p[2];
+                    int ppy = mini(maxi(py + shy + y, 0), h - 1), ppx = mini(maxi(px + shx + x, 0), w - 1);
+                    p = mov3 + 3 * ((size_t)ppy * w + ppx);
+                    meanMov[0] += p[0]; meanMov[1] += p[1]; meanMov[2] += p[2];
+                }
+            for (int c = 0; c < 3; c++) { meanRef[c] /= 9.0f; meanMov[c] /= 9.0f; }
+            float meandist = fabsf(meanRef[0] - meanMov[0]) + fabsf(meanRef[1] - meanMov[1]) + fabsf(meanRef[2] - meanMov[2]);
+            meandist /= 3.0f;
+            maxx *= 0.5f * meandist; maxy *= 0.5f * meandist; minx *= 0.5f * meandist; miny *= 0.5f * meandist;
+            float Mv = sqrtf((maxx - minx) * (maxx - minx) + (maxy - miny) * (maxy - miny));
+            for (int i = 0; i < 9; i++) for (int c = 0; c < 3; c++) stdRef[c] += (pix[i][c] - meanRef[c]) * (pix[i][c] - meanRef[c]);
+            float sigmaMD[3], dist[3], sigma[3], mk[3];
+            for (int c = 0; c < 3; c++) stdRef[c] = sqrtf(stdRef[c] / 9.0f);
+            sigmaMD[0] = sqrtf(alpha * meanRef[0] + beta);
+            sigmaMD[1] = sqrtf(alpha * meanRef[1] + beta) / sqrtf(2.0f);
+            sigmaMD[2] = sqrtf(alpha * meanRef[2] + beta);
+            float s = 1.5f; if (Mv > thresholdM) s = 0;
+            const float tt = 0.12f;
+            for (int c = 0; c < 3; c++) {
+                dist[c] = fabsf(meanRef[c] - meanMov[c]);
+                sigma[c] = fmaxf(sigmaMD[c], stdRef[c]);
+                dist[c] = dist[c] * (stdRef[c] * stdRef[c] / (stdRef[c] * stdRef[c] + sigmaMD[c] * sigmaMD[c]));
+                mk[c] = fmaxf(fminf(s * expf(-dist[c] * dist[c] / (sigma[c] * sigma[c])) - tt, 1.0f), 0.0f);
+            }
+            float* o = mask4 + 4 * ((size_t)py * w + px);
+            o[0] = mk[0]; o[1] = mk[1]; o[2] = mk[2]; o[3] = Mv;
+        }
+}
+/* restated host: (2r+1)^2 min filter on .xyz, clamp border; .w copied */
+void orc_mask_erode(const float* in4, float* out4, int w, int h, int r)
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            float m[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+            for (int dy = -r; dy <= r; dy++)
+                for (int dx = -r; dx <= r; dx++) {
+                    const float* p = in4 + 4 * ((size_t)clampi(y + dy, 0, h - 1) * w + clampi(x + dx, 0, w - 1));
+                    for (int c = 0; c < 3; c++) m[c] = fminf(m[c], p[c]);
+                }
+            float* o = out4 + 4 * ((size_t)y * w + x);
+            o[0] = m[0]; o[1] = m[1]; o[2] = m[2]; o[3] = in4[4 * ((size_t)y * w + x) + 3];
+        }
+}
+
+/* ---- DeBayerKernels.cu:379 accumulateImagesSuperRes (and :290 for s=1) ---
+ * Generalised by orc_merge_geom: the reference is scale=2, out=raw dims,
+ * org=dim/2, clamp=[dim/4, dim/4+dim/2-1].  One frame, read-modify-write. */
+void orc_accumulate(const uint16_t* raw, float* sum3, float* weight3, const float* mask4, const float* kernel4,
+                    const float* flow2, const orc_merge_geom* g, const int cfa[4], const float white[3], const float black[3])
+{
+    int dimX = g->raw_w, dimY = g->raw_h, s = g->scale, mw = dimX / 2;
+#pragma omp parallel for schedule(static)
+    for (int y = 1; y < g->out_h - 1; y++)
+        for (int x = 1; x < g->out_w - 1; x++) {
+            float* pixel = sum3 + 3 * ((size_t)y * g->out_w + x);
+            float* tw = weight3 + 3 * ((size_t)y * g->out_w + x);
+            int X = x + g->org_x, Y = y + g->org_y;
+            float u = ((float)X + 0.5f) / (float)s, v = ((float)Y + 0.5f) / (float)s;
+            float kx = tex_lin(kernel4, dimX, dimY, 4, 0, u, v);
+            float ky = tex_lin(kernel4, dimX, dimY, 4, 1, u, v);
+            float kz = tex_lin(kernel4, dimX, dimY, 4, 2, u, v);
+            float shx = roundf(tex_lin(flow2, dimX, dimY, 2, 0, u, v) * (float)s);
+            float shy = roundf(tex_lin(flow2, dimX, dimY, 2, 1, u, v) * (float)s);
+            int sx = (int)shx, sy = (int)shy;
+            for (int py = -2; py <= 2; py++)
+                for (int px = -2; px <= 2; px++) {
+                    int ppsx = X + px + sx, ppsy = Y + py + sy, ppx = X + px, ppy = Y + py;
+                    ppsx = mini(maxi(ppsx / s, g->clamp_x0), g->clamp_x1);
+                    ppsy = mini(maxi(ppsy / s, g->clamp_y0), g->clamp_y1);
+                    ppx = mini(maxi(ppx / s, g->clamp_x0), g->clamp_x1);
+                    ppy = mini(maxi(ppy / s, g->clamp_y0), g->clamp_y1);
+                    int col = cfa[(ppsy % 2) * 2 + (ppsx % 2)];
+                    float w = px * px * kx + 2 * px * py * kz + py * py * ky;
+                    w = expf(-0.5f * w);
+                    if (!isfinite(w)) w = px * py == 0 ? 1 : 0;
+                    float r = (float)raw[(size_t)ppsy * dimX + ppsx];
+                    if (col >= 0 && col <= 2) {
+                        r = (r - black[col]) / white[col];
+                        float cert = mask4[4 * ((size_t)(ppy / 2) * mw + (ppx / 2)) + col];
+                        if (!isfinite(cert)) cert = 0;
+                        pixel[col] += r * w * cert;
+                        tw[col] += w * cert;
+                    }
+                }
+        }
+}
+/* ---- kernel.cu:426 ApplyWeighting --------------------------------------- */
+void orc_apply_weighting(float* inout3, const float* final3, const float* weight3, int w, int h, float threshold)
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            for (int c = 0; c < 3; c++) {
+                size_t i = 3 * ((size_t)y * w + x) + c;
+                float io = inout3[i], val = final3[i], wt = weight3[i];
+                if (wt < threshold) { val += io; wt += 1; }
+                io = 0;
+                if (wt != 0) io = val / wt;
+                inout3[i] = io;
+            }
+}
+/* ---- kernel.cu:380-422 GammasRGB ---------------------------------------- */
+void orc_gamma_srgb(float* img3, int w, int h)
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; y++)
+        for (size_t i = (size_t)y * w * 3; i < (size_t)(y + 1) * w * 3; i++) {
+            float v = img3[i];
+            if (isnan(v)) v = 0;
+            v = fmaxf(fminf(v, 1.0f), 0.0f);
+            if (v <= 0.0031308f) v = 12.92f * v;
+            else v = (1.0f + 0.055f) * powf(v, 1.0f / 2.4f) - 0.055f;
+            img3[i] = v;
+        }
+}
+/* restated host: fallback image = demosaiced reference sampled on the output grid */
+void orc_fallback_upsample(const float* rgb3, int w, int h, float* out3, const orc_merge_geom* g)
+{
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < g->out_h; y++)
+        for (int x = 0; x < g->out_w; x++) {
+            float u = ((float)(x + g->org_x) + 0.5f) / (float)g->scale, v = ((float)(y + g->org_y) + 0.5f) / (float)g->scale;
+            for (int c = 0; c < 3; c++) out3[3 * ((size_t)y * g->out_w + x) + c] = tex_lin(rgb3, w, h, 3, c, u, v);
+        }
+}

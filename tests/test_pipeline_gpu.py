@@ -1,0 +1,98 @@
+"""End-to-end: mfsr_create / mfsr_set_frames / mfsr_run vs the oracle's stage chain on the same burst."""
+import numpy as np
+import pytest
+import torch
+
+from multi_frame_super_resolution_b200.pipeline import BurstSuperResolution, default_params, measured_pairs
+from multi_frame_super_resolution_b200.synth import synth_burst
+from oracle import pyoracle as O
+from util import max_abs, psnr, u16
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(p, fr, dev, ref_idx=0, host=False):
+    n, h, w = fr.shape
+    sr = BurstSuperResolution(p, device=0, max_width=w, max_height=h, max_frames=n)
+    sr.set_input(u16(fr).copy() if host else fr.to(dev), ref_idx=ref_idx)
+    out = sr.next_frame(host=host)
+    sr.synchronize()
+    return sr, (out.numpy() if host else out.cpu().numpy())
+
+
+@pytest.mark.parametrize("full_frame", [1, 0])
+def test_pipeline_vs_oracle(cuda_device, full_frame):
+    p = default_params()
+    p.full_frame = full_frame
+    p.levels = 3
+    fr, sh = synth_burst(5, 256, 320, seed=77)
+    sr, out = _run(p, fr, cuda_device, ref_idx=2)
+    exp, it = O.run_pipeline(u16(fr), p, ref_idx=2, keep=True)
+    tx, ty, m = sr.tile_grid()
+    assert m == len(measured_pairs(5, p.pair_span)) == len(it["pairs"])
+    # integer tile shifts: bit-exact
+    for k in range(m):
+        assert np.array_equal(sr.tile_argmin(k), it["argmin"][k]), f"pair {k}"
+    # consolidated tile shifts: bit-exact (strict fp32 on both sides)
+    for f in range(5):
+        assert np.array_equal(sr.tile_shifts(f), it["frame_shift"][f])
+    # recovered motion ~ -ground truth (synth: frame(x) = scene(x + d))
+    for f in range(5):
+        med = np.median(sr.tile_shifts(f).reshape(-1, 2), axis=0)
+        gt = -(sh[f] - sh[2]).numpy()
+        assert np.abs(med - gt).max() < 0.35, (f, med, gt)
+    # merged image: tolerance of the north star, allowing isolated round(2*shift) flips caused by
+    # ulp-level differences of atan2f/sinf/cosf inside the LK refinement (counted, must be rare)
+    bad = np.abs(out - exp) > 1e-3
+    assert bad.mean() < 2e-3, f"{bad.mean():.2e} of samples beyond 1e-3"
+    assert psnr(out, exp) >= 50.0
+    st = sr.stage_ms()
+    assert set(st) >= {"frontend", "align", "consolidate", "flow", "kernel_params", "robustness", "fallback", "merge"}
+    assert sr.launch_count() > 20
+    sr.close()
+
+
+def test_pipeline_host_buffers_and_reuse(cuda_device):
+    """Host (pinned/pageable) frames in, host image out, handle reused for a second burst; single frame burst."""
+    p = default_params()
+    p.levels = 2
+    fr, _ = synth_burst(3, 128, 192, seed=5)
+    sr, out_dev = _run(p, fr, cuda_device)
+    sr.set_input(u16(fr).copy(), ref_idx=0)
+    out_host = sr.next_frame(host=True).numpy()
+    assert np.array_equal(out_host, out_dev)
+    fr1, _ = synth_burst(1, 128, 192, seed=6)
+    sr.set_input(fr1.to(cuda_device))
+    o1 = sr.next_frame().cpu().numpy()
+    e1, _ = O.run_pipeline(u16(fr1), p)
+    assert max_abs(o1, e1) <= 1e-3
+    sr.close()
+
+
+def test_pipeline_gray_format(cuda_device):
+    p = default_params()
+    p.levels = 2
+    fr, _ = synth_burst(3, 128, 160, seed=9, bayer=False)
+    n, h, w = fr.shape
+    sr = BurstSuperResolution(p, 0, w, h, n)
+    sr.set_input(fr.to(cuda_device), fmt=1)
+    out = sr.next_frame().cpu().numpy()
+    exp, _ = O.run_pipeline(u16(fr), p, gray_format=True)
+    bad = np.abs(out - exp) > 1e-3
+    assert bad.mean() < 2e-3 and np.all(out[..., 0] == 0)
+    sr.close()
+
+
+def test_api_errors(cuda_device):
+    from multi_frame_super_resolution_b200._lib import MfsrError
+    p = default_params()
+    sr = BurstSuperResolution(p, 0, 128, 128, 2)
+    with pytest.raises(RuntimeError):
+        sr.next_frame()
+    fr, _ = synth_burst(3, 128, 128, seed=1)
+    with pytest.raises(MfsrError):
+        sr.set_input(fr.to(cuda_device))          # more frames than the handle was sized for
+    p2 = default_params(); p2.track_bits = 8      # violates the exact-sum contract for T=16
+    with pytest.raises(MfsrError):
+        BurstSuperResolution(p2, 0, 128, 128, 2).workspace_bytes
+    sr.close()

@@ -1,0 +1,322 @@
+"""Per-stage parity of the CUDA path (through the C ABI) against the oracle, and against the
+reference's own kernels where the prebuilt oracle/_ref library is present.
+
+Bit-exact where the arithmetic is integer or strictly rounded (front end, tracking image,
+pyramid, SSD map, arg-min, tile shifts, upsampling, consolidation inputs); tolerance where
+transcendental functions or re-associated sums are involved (stated per test)."""
+import numpy as np
+import pytest
+import torch
+
+from multi_frame_super_resolution_b200 import stages
+from multi_frame_super_resolution_b200._lib import MergeGeom
+from multi_frame_super_resolution_b200.synth import synth_burst
+from oracle import pyoracle as O
+from oracle import pyref
+from util import BLACK, RGGB, SCALE, max_abs, u16
+
+pytestmark = pytest.mark.gpu
+needs_ref = pytest.mark.skipif(not pyref.available(), reason="oracle/_ref/libmfsr_ref.so not built")
+
+
+@pytest.fixture(scope="module")
+def burst():
+    fr, sh = synth_burst(4, 192, 256, seed=21)
+    return fr, sh
+
+
+def _track(fr_np):
+    out = []
+    for f in range(fr_np.shape[0]):
+        rgb = O.demosaic(fr_np[f], BLACK, SCALE, RGGB)
+        out.append(O.tracking_image(rgb, 0.5, 7))
+    return out
+
+
+def test_subsample3_bit_exact(cuda_device, burst):
+    fr, _ = burst
+    for cfa in (RGGB, [1, 0, 2, 1], [1, 1, 1, 1]):
+        got = stages.subsample3(fr[0].to(cuda_device), 1023.0, cfa).cpu().numpy()
+        assert np.array_equal(got, O.subsample3(u16(fr[0]), 1023.0, cfa))
+
+
+def test_demosaic_bit_exact(cuda_device, burst):
+    fr, _ = burst
+    for cfa in (RGGB, [2, 1, 1, 0], [1, 0, 2, 1]):
+        got = stages.demosaic(fr[1].to(cuda_device), BLACK, SCALE, cfa).cpu().numpy()
+        exp = O.demosaic(u16(fr[1]), BLACK, SCALE, cfa)
+        assert np.array_equal(got, exp)
+    # odd-sized / tiny frames (ragged tiles)
+    small = fr[2, :37, :53].contiguous()
+    assert np.array_equal(stages.demosaic(small.to(cuda_device), BLACK, SCALE, RGGB).cpu().numpy(), O.demosaic(u16(small), BLACK, SCALE, RGGB))
+
+
+@needs_ref
+def test_demosaic_vs_reference_kernels(cuda_device, burst):
+    fr, _ = burst
+    d = fr[1].to(cuda_device)
+    got = stages.demosaic(d, BLACK, SCALE, RGGB).cpu().numpy()
+    ref = pyref.debayer(d, BLACK, SCALE, RGGB).cpu().numpy()
+    assert max_abs(got, ref) <= 2e-6        # FMA contraction in the reference build only
+    sub = stages.subsample3(d, 1023.0, RGGB).cpu().numpy()
+    assert max_abs(sub, pyref.subsample3(d, 1023.0, RGGB).cpu().numpy()) <= 1e-7
+
+
+def test_tracking_image_and_pyramid_bit_exact(cuda_device, burst):
+    fr, _ = burst
+    gray, gq = stages.tracking_image(fr[0].to(cuda_device), BLACK, SCALE, 0.5, 7, RGGB)
+    eg, eq = _track(u16(fr[:1]))[0]
+    assert np.array_equal(gq.cpu().numpy(), eq)
+    assert np.array_equal(gray.cpu().numpy(), eg)
+    assert int(gq.max()) <= 127
+    p1 = stages.pyramid_down(gq)
+    assert np.array_equal(p1.cpu().numpy(), O.pyramid_down(eq))
+    odd = gq[:101, :77].contiguous()
+    assert np.array_equal(stages.pyramid_down(odd).cpu().numpy(), O.pyramid_down(eq[:101, :77]))
+
+
+@pytest.mark.parametrize("T,M", [(16, 4), (16, 2), (8, 4), (32, 8)])
+def test_tile_align_bit_exact(cuda_device, burst, T, M):
+    """SSD map, integer arg-min and sub-pixel tile shifts: bit-exact vs the oracle's fp32 restatement
+    of squaredSum/boxFilter/normalizedCC/findMinimum (exact-sum regime: 7-bit tracking image;
+    T=32 uses a 5-bit image so that 2*T^2*q^2 < 2^24 still holds)."""
+    fr, _ = burst
+    tr = _track(u16(fr[:2]))
+    a, b = tr[0][1], tr[1][1]
+    if T == 32:
+        a, b = a >> 2, b >> 2
+    ty, tx = (a.shape[0] - 2 * M) // T, (a.shape[1] - 2 * M) // T
+    rng = np.random.default_rng(3)
+    pre = (rng.uniform(-3, 3, size=(ty, tx, 2))).astype(np.float32)
+    for p in (None, pre):
+        es, ea, essd = O.tile_align(a, b, p, T, M)
+        gs, ga, gssd = stages.tile_align(torch.from_numpy(a).to(cuda_device), torch.from_numpy(b).to(cuda_device),
+                                         torch.from_numpy(p).to(cuda_device) if p is not None else None, T, M, want_ssd=True)
+        assert np.array_equal(gssd.cpu().numpy(), essd)
+        assert np.array_equal(ga.cpu().numpy(), ea)
+        assert np.array_equal(gs.cpu().numpy(), es)
+
+
+def test_tile_align_ties_and_flat(cuda_device):
+    """Flat tiles: every lag ties -> lowest linear index wins (kernel.cu:536) -> border -> (0,0)."""
+    a = np.full((64, 80), 37, np.uint8)
+    es, ea, _ = O.tile_align(a, a, None, 16, 4)
+    gs, ga, _ = stages.tile_align(torch.from_numpy(a).to(cuda_device), torch.from_numpy(a).to(cuda_device), None, 16, 4)
+    assert np.array_equal(ga.cpu().numpy(), ea) and np.all(ea == -4)
+    assert np.array_equal(gs.cpu().numpy(), es) and np.all(es == 0)
+    # threshold test (kernel.cu:629): threshold + min > max -> (0,0)
+    rng = np.random.default_rng(0)
+    b = rng.integers(0, 127, size=(64, 80), dtype=np.uint8)
+    c = np.roll(b, (1, 2), axis=(0, 1))
+    for thr in (0.0, 1e9):
+        es, ea, _ = O.tile_align(b, c, None, 16, 4, threshold=thr)
+        gs, ga, _ = stages.tile_align(torch.from_numpy(b).to(cuda_device), torch.from_numpy(c).to(cuda_device), None, 16, 4, threshold=thr)
+        assert np.array_equal(gs.cpu().numpy(), es) and np.array_equal(ga.cpu().numpy(), ea)
+    assert np.all(es == 0)
+
+
+@needs_ref
+@pytest.mark.parametrize("use_fft", [False, True])
+def test_tile_align_vs_reference_kernels(cuda_device, burst, use_fft):
+    """Reference chain convertToTiles* -> CC -> squaredSum/boxFilter*/normalizedCC -> findMinimum.
+    Direct CC: integer arg-min bit-exact (exact sums).  cuFFT CC (as upstream): SSD differs by FFT
+    round-off; arg-min mismatches are counted and must be rare near-ties."""
+    fr, _ = burst
+    tr = _track(u16(fr[:2]))
+    a, b = tr[0][1], tr[1][1]
+    T, M = 16, 4
+    da, db = torch.from_numpy(a).to(cuda_device), torch.from_numpy(b).to(cuda_device)
+    gs, ga, gssd = stages.tile_align(da, db, None, T, M, want_ssd=True)
+    coord, rssd = pyref.tile_align(da.float(), db.float(), None, T, M, use_fft=use_fft)
+    S = 2 * M + 1
+    ridx = rssd.argmin(dim=1)          # torch argmin returns the first minimum on ties? verify by value below
+    rarg = torch.stack([ridx % S - M, ridx // S - M], dim=1).cpu().numpy().reshape(ga.shape)
+    g_arg = ga.cpu().numpy()
+    if not use_fft:
+        assert np.array_equal(gssd.cpu().numpy(), rssd.cpu().numpy())
+        assert np.allclose(gs.cpu().numpy(), coord.cpu().numpy(), atol=1e-5)
+        assert np.array_equal(np.floor(gs.cpu().numpy() + 0.5), np.floor(coord.cpu().numpy() + 0.5))
+    else:
+        rel = (gssd - rssd).abs().max().item() / max(1.0, rssd.abs().max().item())
+        assert rel < 1e-5
+        mism = (g_arg != rarg).any(axis=-1).mean()
+        assert mism <= 0.01, f"arg-min mismatch vs cuFFT path on {mism:.3%} of tiles"
+
+
+def test_upsample_shifts_bit_exact(cuda_device):
+    rng = np.random.default_rng(1)
+    coarse = rng.uniform(-4, 4, size=(5, 7, 2)).astype(np.float32)
+    for (ncx, ncy) in ((15, 11), (14, 10), (7, 5)):
+        exp = O.upsample_shifts(coarse, 4, 2, ncx, ncy, 16, 16)
+        got = stages.upsample_shifts(torch.from_numpy(coarse).to(cuda_device), 4, 2, ncx, ncy, 16, 16).cpu().numpy()
+        assert np.array_equal(got, exp)
+
+
+@needs_ref
+def test_upsample_shifts_vs_reference_kernel(cuda_device):
+    rng = np.random.default_rng(2)
+    coarse = torch.from_numpy(rng.uniform(-4, 4, size=(6, 9, 2)).astype(np.float32)).to(cuda_device)
+    got = stages.upsample_shifts(coarse, 8, 4, 19, 13, 16, 16).cpu().numpy()
+    ref = pyref.upsample_shifts(coarse, 8, 4, 19, 13, 16, 16).cpu().numpy()
+    assert max_abs(got, ref) <= 1e-5
+
+
+def _pairs(n, span):
+    return [(i, j) for i in range(n) for j in range(i + 1, min(n, i + span + 1))]
+
+
+@pytest.mark.parametrize("n,span", [(2, 1), (5, 2), (8, 2), (8, 7), (15, 2)])
+def test_consolidate_shifts(cuda_device, n, span):
+    """Consistent measurements are reproduced; injected outliers are removed; bit-exact vs oracle."""
+    rng = np.random.default_rng(n * 10 + span)
+    pairs = _pairs(n, span)
+    tx, ty = 9, 7
+    nt = tx * ty
+    seq = rng.uniform(-2, 2, size=(nt, n - 1, 2)).astype(np.float32)
+    meas = np.zeros((nt, len(pairs), 2), np.float32)
+    for k, (i, j) in enumerate(pairs):
+        meas[:, k] = seq[:, i:j].sum(axis=1)
+    meas += rng.normal(0, 0.02, size=meas.shape).astype(np.float32)
+    if len(pairs) > n:                      # redundancy available: corrupt one measurement in a third of the tiles
+        bad = rng.integers(0, len(pairs), size=nt)
+        for t in range(0, nt, 3):
+            meas[t, bad[t]] += 7.0
+    pf, pt = [a for a, _ in pairs], [b for _, b in pairs]
+    ref_img = n // 2
+    e1, efs, est = O.consolidate_shifts(meas, pf, pt, n, tx, ty, ref_img)
+    g1, gfs, gst = stages.consolidate_shifts(torch.from_numpy(meas).to(cuda_device), pf, pt, n, tx, ty, ref_img)
+    assert np.array_equal(gst.cpu().numpy(), est)
+    assert np.array_equal(g1.cpu().numpy(), e1)
+    assert np.array_equal(gfs.cpu().numpy(), efs)
+    if len(pairs) > n:
+        clean = np.ones(nt, bool); clean[::3] = False
+        assert np.abs(e1[clean] - seq[clean]).max() < 0.2
+        assert (est[::3] >= 1).mean() > 0.9
+
+
+def test_flow_from_tiles(cuda_device):
+    rng = np.random.default_rng(4)
+    tiles = rng.uniform(-3, 3, size=(11, 15, 2)).astype(np.float32)
+    w, h = 15 * 16 + 8, 11 * 16 + 8
+    got = stages.flow_from_tiles(torch.from_numpy(tiles).to(cuda_device), 16, w, h).cpu().numpy()
+    exp = O.flow_from_tiles(tiles, 16, w, h)
+    assert np.array_equal(got, exp)
+    got = stages.flow_from_tiles(torch.from_numpy(tiles).to(cuda_device), 16, w, h, (1.5, -2.0), 0.02).cpu().numpy()
+    assert max_abs(got, O.flow_from_tiles(tiles, 16, w, h, (1.5, -2.0), 0.02)) <= 1e-4     # sinf/cosf differ by ulps
+
+
+@needs_ref
+def test_flow_from_tiles_vs_reference_kernel(cuda_device):
+    rng = np.random.default_rng(5)
+    tiles = torch.from_numpy(rng.uniform(-3, 3, size=(11, 15, 2)).astype(np.float32)).to(cuda_device)
+    w, h = 248, 184
+    got = stages.flow_from_tiles(tiles, 16, w, h).cpu().numpy()
+    ref = pyref.flow_from_tiles(tiles, 16, w, h).cpu().numpy()
+    # hardware texture filtering: 1.8 fixed-point fraction; the model rounds to nearest 1/256
+    assert max_abs(got, ref) <= 6.0 / 256.0 and np.mean(np.abs(got - ref)) < 2e-3
+
+
+def test_lk_iteration_vs_oracle(cuda_device, burst):
+    """Tolerance: window sums are re-associated (row sums then column sums) and atan2f/sinf/cosf
+    differ by ulps between CUDA and glibc -> max-abs 2e-3 px on the flow update."""
+    fr, sh = burst
+    tr = _track(u16(fr[:2]))
+    ref, mov = tr[0][0], tr[1][0]
+    h, w = ref.shape
+    flow = np.zeros((h, w, 2), np.float32)
+    flow[..., 0], flow[..., 1] = -sh[1, 0].item() + 0.3, -sh[1, 1].item() - 0.2
+    for hw in (3, 2):
+        exp = O.lk_iteration(ref, mov, flow, hw, 1e-3)
+        got = stages.lk_iteration(torch.from_numpy(ref).to(cuda_device), torch.from_numpy(mov).to(cuda_device),
+                                  torch.from_numpy(flow).to(cuda_device), hw, 1e-3).cpu().numpy()
+        d = np.abs(got - exp)
+        assert np.percentile(d, 99.9) <= 2e-3, float(d.max())
+        assert np.array_equal(got[:hw], flow[:hw]) and np.array_equal(got[:, -hw:], flow[:, -hw:])   # untouched border (:205)
+
+
+@needs_ref
+def test_lk_iteration_vs_reference_kernels(cuda_device, burst):
+    fr, sh = burst
+    tr = _track(u16(fr[:2]))
+    ref, mov = torch.from_numpy(tr[0][0]).to(cuda_device), torch.from_numpy(tr[1][0]).to(cuda_device)
+    h, w = ref.shape
+    flow = torch.zeros((h, w, 2), device=cuda_device)
+    flow[..., 0], flow[..., 1] = -sh[1, 0].item() + 0.3, -sh[1, 1].item() - 0.2
+    got = stages.lk_iteration(ref, mov, flow, 3, 1e-3)
+    exp = pyref.lk_iteration(ref, mov, flow, 3, 1e-3)
+    d = (got - exp).abs()
+    assert float(torch.quantile(d.flatten()[:: 7], 0.999)) <= 2e-2     # texture-unit bilinear in the warp
+
+
+def test_kernel_params_vs_oracle(cuda_device, burst):
+    fr, _ = burst
+    gray = _track(u16(fr[:1]))[0][0]
+    for r in (2, 0, 1):
+        exp = O.kernel_params(gray, r)
+        got = stages.kernel_params(torch.from_numpy(gray).to(cuda_device), r).cpu().numpy()
+        rel = np.abs(got - exp) / (np.abs(exp) + 1e-3)
+        assert np.percentile(rel, 99.9) < 1e-3 and np.isfinite(got).all() == np.isfinite(exp).all()
+
+
+@needs_ref
+def test_kernel_params_vs_reference_kernels(cuda_device, burst):
+    fr, _ = burst
+    gray = torch.from_numpy(_track(u16(fr[:1]))[0][0]).to(cuda_device)
+    ix, iy = pyref.derivatives2(gray)
+    t3 = pyref.structure_tensor(ix, iy)
+    ref = pyref.kernel_param(t3, 0.005, 0.012, 0.3, 4.0, 4.0, 2.0).cpu().numpy()
+    got = stages.kernel_params(gray, 0).cpu().numpy()[..., :3]
+    rel = np.abs(got - ref) / (np.abs(ref) + 1e-3)
+    assert np.percentile(rel, 99.9) < 1e-3
+
+
+def test_robustness_vs_oracle(cuda_device, burst):
+    fr, sh = burst
+    a = O.subsample3(u16(fr[0]), 1023.0, RGGB)
+    b = O.subsample3(u16(fr[1]), 1023.0, RGGB)
+    h2, w2 = a.shape[:2]
+    ys, xs = np.mgrid[0:2 * h2, 0:2 * w2].astype(np.float32)
+    flow = np.stack([-sh[1, 0].item() + 0.4 * np.sin(xs / 37.0), -sh[1, 1].item() + 0.5 * np.cos(ys / 29.0)], -1).astype(np.float32)
+    for er in (0, 2):
+        exp = O.robustness_mask(a, b, flow, 1e-3, 1e-5, 0.8, er)
+        got = stages.robustness(torch.from_numpy(a).to(cuda_device), torch.from_numpy(b).to(cuda_device),
+                                torch.from_numpy(flow).to(cuda_device), 1e-3, 1e-5, 0.8, er).cpu().numpy()
+        assert max_abs(got, exp) <= 1e-4
+        assert np.all(got[0, :, :3] == 0) and np.all(got[:, 0, :3] == 0)       # unwritten border (:48)
+
+
+@needs_ref
+def test_robustness_vs_reference_kernel(cuda_device, burst):
+    fr, sh = burst
+    d0, d1 = fr[0].to(cuda_device), fr[1].to(cuda_device)
+    a, b = stages.subsample3(d0, 1023.0, RGGB), stages.subsample3(d1, 1023.0, RGGB)
+    h2, w2 = a.shape[:2]
+    flow = torch.zeros((2 * h2, 2 * w2, 2), device=cuda_device)
+    flow[..., 0], flow[..., 1] = -sh[1, 0].item(), -sh[1, 1].item()
+    got = stages.robustness(a, b, flow, 1e-3, 1e-5, 0.8, 0).cpu().numpy()
+    ref = pyref.robustness_mask(a, b, flow, 1e-3, 1e-5, 0.8).cpu().numpy()
+    assert max_abs(got, ref) <= 1e-4
+
+
+def test_fallback_upsample(cuda_device, burst):
+    fr, _ = burst
+    rgb = O.demosaic(u16(fr[0]), BLACK, SCALE, RGGB)
+    h, w = rgb.shape[:2]
+    for geom in (MergeGeom.reference(w, h), MergeGeom.full_frame(w, h, 3)):
+        got = stages.fallback_upsample(torch.from_numpy(rgb).to(cuda_device), geom).cpu().numpy()
+        assert np.array_equal(got, O.fallback_upsample(rgb, O.Geom.from_product(geom)))
+
+
+@needs_ref
+def test_texture_model_probe(cuda_device):
+    """Pins the texture model: linear-filtered fetches of a ramp at the quarter positions the merge
+    uses (DeBayerKernels.cu:398) and at arbitrary positions (warp)."""
+    w = 4032
+    tex = torch.arange(w, dtype=torch.float32, device=cuda_device)
+    x = torch.arange(1, 2 * w - 1, device=cuda_device, dtype=torch.float32)
+    xn = ((x + 0.5) / 2.0 / w)                       # merge: posX for an output pixel (window origin 0)
+    got = pyref.texture_probe(tex, xn.contiguous()).cpu().numpy()
+    exact = (x.cpu().numpy() + 0.5) / 2.0 - 0.5      # ramp value == unnormalised coordinate - 0.5
+    frac_err = np.abs(got - exact)
+    assert frac_err.max() <= 1.0 / 256.0 + 1e-6, frac_err.max()
+    print("texture probe quarter positions: max |hw - exact| =", frac_err.max(), "mean", frac_err.mean())
