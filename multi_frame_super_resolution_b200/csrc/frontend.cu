@@ -2,7 +2,7 @@
 //
 // Compiled with -fmad=false (see build.py): the 7-bit tracking image feeds the
 // integer block matcher, so its fp32 arithmetic must round exactly like a strict
-// IEEE evaluation of the same formulas (oracle/mfsr_oracle.c) — then the integer
+// IEEE evaluation of the same formulas on a CPU — then the integer
 // tile shifts are bit-exact by construction.  These kernels are HBM-bound
 // (2 B in, 4..12 B out per pixel); the lost FMA contraction costs nothing.
 //

@@ -148,7 +148,8 @@ extern "C" int mfsr_stage_merge(const uint16_t* raw, int64_t raw_pitch, int64_t 
                                 const float white[3], const float black[3],
                                 float threshold, int flags, void* stream)
 {
-    if (!raw || !mask || !flow || !kernel4 || !out || !geom || !cfa || !white || !black) return MFSR_E_INVALID;
+    if (!kernel4 || !out || !geom || !cfa || !white || !black) return MFSR_E_INVALID;
+    if (n_frames > 0 && (!raw || !mask || !flow)) return MFSR_E_INVALID;
     if (n_frames < 0 || geom->scale < 1 || geom->out_w <= 0 || geom->out_h <= 0) return MFSR_E_INVALID;
     if (!fallback && !(flags & MFSR_MERGE_NO_FALLBACK)) return MFSR_E_INVALID;
     if ((sum_out == nullptr) != (weight_out == nullptr)) return MFSR_E_INVALID;

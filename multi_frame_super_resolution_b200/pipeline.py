@@ -80,6 +80,9 @@ class BurstSuperResolution:
             check(self._lib.mfsr_create(C.byref(self.params), self.device, *self._max, C.byref(h)), "mfsr_create")
             self._h = h
 
+    def _ext(self):
+        return torch.cuda.ExternalStream(self.stream, device=torch.device("cuda", self.device))
+
     def _destroy(self):
         if self._h:
             self._lib.mfsr_destroy(self._h)
@@ -123,6 +126,9 @@ class BurstSuperResolution:
                 raise ValueError("frames must be a contiguous 16-bit tensor [N,H,W]")
             n, h, w = frames.shape
             base, on_host = frames.data_ptr(), 0 if frames.is_cuda else 1
+        if not on_host:
+            # the frames were produced on torch's current stream: order the handle's stream after it
+            self._ext().wait_stream(torch.cuda.current_stream(self.device))
         ptrs = (C.c_void_p * n)(*[base + i * h * w * 2 for i in range(n)])
         check(self._lib.mfsr_set_frames(self._h, ptrs, n, w, h, w * 2, fmt, ref_idx, on_host), "mfsr_set_frames")
         self._shape = (h, w)
@@ -143,6 +149,8 @@ class BurstSuperResolution:
         if out is None:
             out = torch.empty((oh, ow, 3), dtype=torch.float32, device=f"cuda:{self.device}")
         check(self._lib.mfsr_run(self._h, C.c_void_p(out.data_ptr()), ow * 12, 0), "mfsr_run")
+        # asynchronous, but ordered: whoever consumes `out` on torch's current stream sees the finished image
+        torch.cuda.current_stream(self.device).wait_stream(self._ext())
         return out
 
     def synchronize(self):

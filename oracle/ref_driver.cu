@@ -28,6 +28,11 @@
 #include "DeBayerKernels.cu"
 #include "RobustnessModell.cu"
 
+/* DeBayerKernels.cu:40-41 only DECLARES the CFA table (`extern "C" __device__ __constant__ ...;` —
+ * upstream's host loads the kernels as a PTX module and the symbol is defined elsewhere there);
+ * the restated host supplies the definition. */
+extern "C" { __device__ __constant__ BayerColor c_cfaPattern[2][2] = {{Red, Green}, {Green, Blue}}; }
+
 #define RTRY(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { fprintf(stderr, "ref_driver: %s at %s:%d\n", cudaGetErrorString(_e), __FILE__, __LINE__); return (int)_e; } } while (0)
 #define RSYNC() do { RTRY(cudaGetLastError()); RTRY(cudaDeviceSynchronize()); } while (0)
 

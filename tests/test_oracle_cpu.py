@@ -1,0 +1,129 @@
+"""Known-answer and property tests of the oracle itself (CPU only), incl. BASELINE config 1
+(the reference's bundled 5-frame burst, mosaiced: tests/golden/bundled_burst_rggb.npz)."""
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+
+WHITE, BLACK = [959.0, 959.0, 959.0], [64.0, 64.0, 64.0]
+RGGB = [0, 1, 1, 2]
+
+
+def params(**kw):
+    d = dict(scale=2, full_frame=1, cfa=RGGB, black_level=BLACK, white_level=WHITE, tile_size=16, max_shift=4, levels=3,
+             pair_span=2, track_bits=7, track_sigma=0.5, min_threshold=0.0, base_shift=[0.0, 0.0], base_rotation=0.0,
+             lk_iterations=3, lk_half_window=3, lk_min_det=1e-3, Dth=0.005, Dtr=0.012, kDetail=0.3, kDenoise=4.0, kStretch=4.0,
+             kShrink=2.0, tensor_box_radius=2, alpha=1e-3, beta=1e-5, thresholdM=0.8, mask_erode_radius=2,
+             weight_threshold=0.1, merge_flags=0)
+    d.update(kw)
+    return SimpleNamespace(**d)
+
+
+def test_gauss_taps_match_reference_rule():
+    t = O.gauss_taps(0.5)                       # size = (int)(0.5/0.6 - 0.4)*2 + 3 = 3 (main.cpp:374)
+    assert len(t) == 3 and abs(t.sum() - 1) < 1e-6 and t[0] == t[2]
+    assert abs(t[0] / t[1] - np.exp(-2.0)) < 1e-6
+    assert len(O.gauss_taps(2.0)) == 7 and len(O.gauss_taps(0.0)) == 9 and O.gauss_taps(0.0)[4] == 1
+
+
+def test_gamma_known_answers():
+    v = np.array([[[-1.0, 0.0, 0.002], [0.0031308, 0.5, 1.0], [2.0, np.nan, 0.2]]], np.float32)
+    g = O.gamma_srgb(v)
+    exp = [0, 0, 12.92 * 0.002, 12.92 * 0.0031308, 1.055 * 0.5 ** (1 / 2.4) - 0.055, 1.0, 1.0, 0.0, 1.055 * 0.2 ** (1 / 2.4) - 0.055]
+    assert np.allclose(g.ravel(), exp, atol=1e-6)
+
+
+def test_apply_weighting_cases():
+    io = np.full((1, 4, 3), 0.5, np.float32)
+    fin = np.array([[[2.0] * 3, [0.02] * 3, [0.0] * 3, [1.0] * 3]], np.float32)
+    w = np.array([[[4.0] * 3, [0.05] * 3, [0.0] * 3, [-1.0] * 3]], np.float32)
+    out = O.apply_weighting(io, fin, w, 0.1)
+    assert np.allclose(out[0, 0], 0.5)                                # plain normalisation 2/4
+    assert np.allclose(out[0, 1], (0.02 + 0.5) / 1.05)                # below threshold: blend in the reference image
+    assert np.allclose(out[0, 2], 0.5)                                # no data: reference image
+    assert np.all(out[0, 3] == 0)                                     # w + 1 == 0 -> 0 (kernel.cu:452-456)
+
+
+def test_find_minimum_subpixel_and_quirks():
+    S, M = 9, 4
+    ys, xs = np.mgrid[0:S, 0:S].astype(np.float32)
+    ssd = (3.0 * (xs - 5.3) ** 2 + 2.0 * (ys - 2.6) ** 2 + 10).reshape(1, -1)
+    c, a = O.find_minimum(ssd, M)
+    assert tuple(a[0]) == (1, -1) and np.allclose(c[0], [5.3 - 4, 2.6 - 4], atol=1e-4)
+    border = ((xs - 0.2) ** 2 + (ys - 4) ** 2).reshape(1, -1)        # minimum on the border -> (0,0) (:548)
+    c, a = O.find_minimum(border, M)
+    assert tuple(a[0]) == (-4, 0) and np.all(c == 0)
+    flat = np.full((1, S * S), 7.0, np.float32)                      # ties -> lowest linear index (:536)
+    c, a = O.find_minimum(flat, M)
+    assert tuple(a[0]) == (-4, -4)
+    c, _ = O.find_minimum(ssd, M, threshold=1e9)                     # threshold + min > max -> (0,0) (:629)
+    assert np.all(c == 0)
+
+
+def test_cross_correlation_is_circular_and_tile_align_recovers_shift():
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 100, size=(2, 12, 12)).astype(np.float32)
+    b = np.roll(a, (2, -3), axis=(1, 2))
+    cc = O.cross_correlation(a, b)
+    assert np.all(cc.reshape(2, -1).argmax(1) == 2 * 12 + 9)          # lag (+2, -3) in fft layout
+    img = rng.integers(0, 128, size=(80, 96)).astype(np.uint8)
+    mov = np.roll(img, (1, -2), axis=(0, 1))                          # ref(p) = mov(p + (-2, +1))
+    shift, arg, ssd = O.tile_align(img, mov, None, 16, 4)
+    assert np.all(arg[..., 0] == -2) and np.all(arg[..., 1] == 1) and np.all(ssd.min(axis=1) == 0)
+    assert np.allclose(shift, arg, atol=0.05)                          # sub-pixel fit of a random surface: ~0
+    pre = np.full(arg.shape, 0.0, np.float32); pre[..., 0] = -1.6; pre[..., 1] = 1.4
+    shift2, arg2, _ = O.tile_align(img, mov, pre, 16, 4)              # patch displaced by round(pre) = (-2, 1)
+    assert np.all(arg2 == 0) and np.allclose(shift2, [-2, 1], atol=0.05)
+
+
+def test_upsample_shifts_scales_and_interpolates():
+    coarse = np.zeros((3, 4, 2), np.float32); coarse[..., 0] = np.arange(4); coarse[..., 1] = 2
+    up = O.upsample_shifts(coarse, 4, 2, 8, 6, 16, 16)
+    assert np.allclose(up[..., 1], 4) and np.allclose(up[0, :7, 0], np.arange(7))        # values x2, positions /2
+
+
+def test_consolidation_exact_and_outlier():
+    pairs = [(i, j) for i in range(5) for j in range(i + 1, min(5, i + 3))]
+    seq = np.array([[1.0, -1], [0.5, 2], [-2, 0.25], [0.75, 0.5]], np.float32)
+    meas = np.array([[seq[i:j].sum(0) for i, j in pairs]], np.float32)
+    one, fs, st = O.consolidate_shifts(meas, [a for a, _ in pairs], [b for _, b in pairs], 5, 1, 1, 2)
+    assert st[0] == 0 and np.allclose(one[0], seq, atol=1e-5)
+    assert np.allclose(fs[4, 0, 0], seq[2:4].sum(0), atol=1e-5) and np.allclose(fs[0, 0, 0], -seq[0:2].sum(0), atol=1e-5)
+    meas[0, 3] += 5
+    one, fs, st = O.consolidate_shifts(meas, [a for a, _ in pairs], [b for _, b in pairs], 5, 1, 1, 2)
+    assert st[0] == 1 and np.allclose(one[0], seq, atol=1e-5)
+
+
+def test_merge_delta_kernel_picks_nearest_raw_sample():
+    h, w = 32, 48
+    rng = np.random.default_rng(1)
+    raw = rng.integers(64, 1023, size=(1, h, w), dtype=np.uint16)
+    mask = np.ones((1, h // 2, w // 2, 4), np.float32)
+    flow = np.zeros((1, h, w, 2), np.float32)
+    kern = np.zeros((h, w, 4), np.float32); kern[..., 0] = kern[..., 1] = 1e4       # exp(-5000 r^2): only the centre tap
+    g = O.Geom.full_frame(w, h, 2)
+    out, s, wt = O.merge(raw, mask, flow, kern, None, g, WHITE, BLACK, 0.1, RGGB, want_accumulators=True)
+    X, Y = 20, 12                                                                   # raw sample (10, 6): R site
+    assert wt[Y, X, 0] == 1 and wt[Y, X, 1] == 0 and s[Y, X, 0] == np.float32((raw[0, 6, 10] - 64.0) / 959.0)
+    # linearity in the certainty
+    out2, s2, wt2 = O.merge(raw, mask * 0.5, flow, kern, None, g, WHITE, BLACK, 0.1, RGGB, want_accumulators=True)
+    assert np.array_equal(s2, s * 0.5) and np.array_equal(wt2, wt * 0.5)
+
+
+def test_bundled_burst_config1():
+    """BASELINE configs[0]: the reference's own 5-frame burst.  Frames 2-4 are rotated 5/10/-15 degrees
+    (main.cpp:1894-1907); without the global pre-alignment stage they cannot align and the
+    robustness model must reject them, while frame 1 (pure shift) aligns."""
+    fr = np.load(Path(__file__).resolve().parent / "golden" / "bundled_burst_rggb.npz")["frames"]
+    assert fr.shape == (5, 256, 512)
+    out, it = O.run_pipeline(fr, params(), ref_idx=0, keep=True)
+    assert out.shape == (512, 1024, 3) and np.isfinite(out).all()
+    med = np.median(it["frame_shift"][1].reshape(-1, 2), axis=0)
+    assert np.abs(np.abs(med) - [1, 3]).max() < 0.5, med            # frame 1 ~ shift (-1,-3) px
+    m = [it["mask"][f][..., :3].mean() for f in range(5)]
+    assert m[0] > 0.85 and m[1] > 0.4 and m[1] > m[2] > m[3] > m[4] and m[4] < 0.1, m   # certainty falls with rotation
+    fb = it["fallback"]
+    assert 20 < 10 * np.log10(1.0 / np.mean((out - fb) ** 2)) < 60   # close to, but not identical with, the demosaiced reference

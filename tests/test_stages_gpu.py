@@ -213,7 +213,9 @@ def test_flow_from_tiles_vs_reference_kernel(cuda_device):
     got = stages.flow_from_tiles(tiles, 16, w, h).cpu().numpy()
     ref = pyref.flow_from_tiles(tiles, 16, w, h).cpu().numpy()
     # hardware texture filtering: 1.8 fixed-point fraction; the model rounds to nearest 1/256
-    assert max_abs(got, ref) <= 6.0 / 256.0 and np.mean(np.abs(got - ref)) < 2e-3
+    # (matches the hardware on 100 % of quarter positions and ~97 % of arbitrary ones, rest off by one LSB: see
+    #  tests/test_oracle_golden.py::test_texture_model); neighbouring tile shifts differ by up to 6 px here
+    assert max_abs(got, ref) <= 6.0 / 256.0 and np.mean(np.abs(got - ref)) < 4e-3
 
 
 def test_lk_iteration_vs_oracle(cuda_device, burst):
@@ -254,8 +256,11 @@ def test_kernel_params_vs_oracle(cuda_device, burst):
     for r in (2, 0, 1):
         exp = O.kernel_params(gray, r)
         got = stages.kernel_params(torch.from_numpy(gray).to(cuda_device), r).cpu().numpy()
-        rel = np.abs(got - exp) / (np.abs(exp) + 1e-3)
-        assert np.percentile(rel, 99.9) < 1e-3 and np.isfinite(got).all() == np.isfinite(exp).all()
+        # gray == 0 in the 2-px demosaic border -> tensor 0 -> 0/0 in ComputeKernelParam (kernel.cu:761) on both sides
+        assert np.array_equal(np.isfinite(got), np.isfinite(exp))
+        fin = np.isfinite(exp)
+        rel = np.abs(got[fin] - exp[fin]) / (np.abs(exp[fin]) + 1e-3)
+        assert np.percentile(rel, 99.9) < 1e-3
 
 
 @needs_ref
@@ -266,7 +271,9 @@ def test_kernel_params_vs_reference_kernels(cuda_device, burst):
     t3 = pyref.structure_tensor(ix, iy)
     ref = pyref.kernel_param(t3, 0.005, 0.012, 0.3, 4.0, 4.0, 2.0).cpu().numpy()
     got = stages.kernel_params(gray, 0).cpu().numpy()[..., :3]
-    rel = np.abs(got - ref) / (np.abs(ref) + 1e-3)
+    assert np.array_equal(np.isfinite(got), np.isfinite(ref))
+    fin = np.isfinite(ref)
+    rel = np.abs(got[fin] - ref[fin]) / (np.abs(ref[fin]) + 1e-3)
     assert np.percentile(rel, 99.9) < 1e-3
 
 
