@@ -10,41 +10,10 @@
 //   merge_generic_kernel  any scale / geometry, one thread per output pixel,
 //                         direct global gathers.  Reference semantics, simple.
 //   merge_s2_kernel       scale 2 fast path (see below).
-#include "common.cuh"
+#include "merge_common.cuh"
+#include <stdlib.h>
 
 namespace mfsr {
-
-struct MergeArgs {
-    const uint16_t* raw;  int64_t raw_pitch,  raw_fs;
-    const float4*   mask; int64_t mask_pitch, mask_fs;
-    const float2*   flow; int64_t flow_pitch, flow_fs;
-    const float4*   kern; int64_t kern_pitch;
-    const float*    fallback; int64_t fb_pitch;
-    float*          out;  int64_t out_pitch;
-    float*          sum_out; float* weight_out; int64_t acc_pitch;
-    int n_frames;
-    mfsr_merge_geom g;
-    Cfa cfa;
-    float white[3], black[3];
-    float threshold;
-    int flags;
-};
-
-// ApplyWeighting (kernel.cu:426) for one channel; `fb` is the reference's inOutImg value.
-__device__ __forceinline__ float apply_weighting(float val, float w, float fb, float threshold)
-{
-    if (w < threshold) { val += fb; w += 1.0f; }
-    return (w != 0.0f) ? val / w : 0.0f;
-}
-__device__ __forceinline__ float finish_px(float v, int flags)
-{
-    if (flags & MFSR_MERGE_GAMMA) {                // GammasRGB (kernel.cu:393)
-        if (isnan(v)) v = 0.0f;
-        v = fmaxf(fminf(v, 1.0f), 0.0f);
-        v = srgb_gamma(v);
-    }
-    return v;
-}
 
 __global__ void __launch_bounds__(256)
 merge_generic_kernel(const __grid_constant__ MergeArgs A)
@@ -167,6 +136,12 @@ extern "C" int mfsr_stage_merge(const uint16_t* raw, int64_t raw_pitch, int64_t 
     for (int i = 0; i < 4; i++) A.cfa.c[i] = cfa[i];
     for (int i = 0; i < 3; i++) { A.white[i] = white[i]; A.black[i] = black[i]; }
     A.threshold = threshold; A.flags = flags;
+    // scale-2 fast path (merge_fast.cu); MFSR_MERGE_GENERIC=1 forces the generic kernel (A/B tests)
+    static const bool force_generic = getenv("MFSR_MERGE_GENERIC") != nullptr;
+    if (geom->scale == 2 && n_frames > 0 && !force_generic) {
+        const int rc = launch_merge_s2(A, (cudaStream_t)stream);
+        if (rc != MFSR_E_INVALID) return rc;
+    }
     dim3 block(32, 8), grid(cdiv(geom->out_w, 32), cdiv(geom->out_h, 8));
     merge_generic_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(A);
     MFSR_LAUNCH_CHECK();

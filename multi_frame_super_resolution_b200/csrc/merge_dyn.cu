@@ -1,0 +1,457 @@
+// merge_dyn.cu — scale-2 kernel-regression merge for PER-PIXEL shifts (the production scale-2 kernel).
+//
+// Same arithmetic as merge_generic_kernel (N x accumulateImagesSuperRes DeBayerKernels.cu:379-468 +
+// ApplyWeighting kernel.cu:426 + GammasRGB kernel.cu:393).  Measured on real pipeline flows the integer
+// HR shift round(2*flow) differs between horizontally adjacent output pixels in ~26 % of 4-pixel groups
+// (Lucas-Kanade noise), so a warp never sees one shift parity: the static (RHO, EY) specialisation of
+// merge_fast.cu diverges.  Here nothing branches on the shift:
+//
+//  * warp w owns row w of the tile and runs four passes J = 0..3; in a pass lane l owns the output pixel at
+//    absolute HR column 4B + J, so (J = X%4, YM = Y%4) — which certainty sample each of the
+//    25 taps reads — are compile-time, every warp scheduler (warp % 4 == YM) executes ONE code variant
+//    and at most four variants are live per SM (the first version, with 8 variants interleaved on an SM,
+//    stalled 23 of 24 issue slots on instruction fetch: profiles/r1b_merge_dyn_icache_ncu.txt);
+//  * which raw sample a tap reads depends on the parity of X+sx / Y+sy only for the taps at +-1: those
+//    taps are issued once per candidate destination under a lane predicate (49 predicated FMAs instead
+//    of 25) and fold into a 3x3 per-raw-sample weight G, then 18 FMAs accumulate value and weight;
+//  * the CFA phase of the window centre only permutes certainty channels and accumulators: certainty is
+//    staged in four channel-permuted planes and fetched with a phase-dependent ADDRESS, the four class
+//    sums are routed to absolute-phase accumulators by a 2-level select.
+//  * raw windows are staged once per tile and frame as normalised float, de-interleaved by column
+//    parity so that a warp's stride-2 window reads are bank-conflict free.
+//  * the staged raw window is centred on the tile's MEAN shift; a pixel whose own window falls outside
+//    it (alignment outliers) fetches its 3x3 raw samples from global memory instead, same code after.
+// Taps that hit the clamp range (:414-419) and shifts beyond +-127 take the per-pixel generic path of
+// merge_s2_common.cuh.
+#include "merge_s2_common.cuh"
+
+namespace mfsr {
+
+namespace {
+
+using namespace s2;
+
+constexpr int RHALF = RWS / 2;   // odd raw columns live RHALF floats after the even ones of the same row
+
+template <int TH> struct DCfg {
+    static constexpr int NW_ = TH;                   // warps: one per tile row
+    static constexpr int NT = 32 * TH;               // threads
+    static constexpr int RHS = TH / 2 + 7;           // staged raw rows (TH/2 + taps 3 + slack 4)
+    static constexpr int MHS = TH / 4 + 2;           // staged certainty rows
+    static constexpr int PLANE = MHS * MWS;          // float2 elements per certainty plane
+    static constexpr int SHIFT_BYTES = TH * TW * 2;
+    static constexpr int RAW_BYTES = RHS * RWS * 4;
+    static constexpr int MASK_BYTES = 4 * PLANE * 8;
+    static constexpr int FRAME_BYTES = SHIFT_BYTES + RAW_BYTES + MASK_BYTES;
+    static constexpr int KWS = TW / 2 + 2, KHS = TH / 2 + 2;      // staged kernel-parameter window (raw resolution + 1 each side)
+    static constexpr int KERN_BYTES = KWS * KHS * 16;
+};
+
+MFSR_CX int g_e(int e, int p) { return mt::fl2(e + p); }      // raw sample of tap p relative to the window centre
+
+// g = fma(w, c, g) under a lane predicate (p != 0).  Inline PTX keeps ptxas from turning the 40 conditional
+// taps into FSEL + FFMA pairs (it did: 48 FSEL per pixel and frame in profiles/r1c).
+__device__ __forceinline__ void pfma(float& g, float w, float c, int p)
+{
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\t@q fma.rn.f32 %0, %1, %2, %0;\n\t}" : "+f"(g) : "f"(w), "f"(c), "r"(p));
+}
+__device__ __forceinline__ int bfe_s8(unsigned v, int pos)
+{
+    int r;
+    asm("bfe.s32 %0, %1, %2, 8;" : "=r"(r) : "r"(v), "r"(pos));
+    return r;
+}
+
+// One pixel, one frame, everything in shared memory.  J = X % 4 and YM = Y % 4 are static; the parities of
+// X+sx / Y+sy (ex, ey) are lane predicates; the CFA phase of the window centre only moves addresses (pe/po,
+// q0/q1) and the final routing (phx, phy).
+//   pe : staged raw sample (ky-1, k-1); (ky-1, k+1) is the next float (de-interleaved rows)   po : (ky-1, k)
+//   q0 / q1 : certainty planes of y class 0 / 1 at the thread's first mask pixel
+template <int J, int YM>
+__device__ __forceinline__ void pixel_fast(const float (&w)[mt::NW], const float* __restrict__ pe, const float* __restrict__ po,
+                                           const float2* __restrict__ q0, const float2* __restrict__ q1,
+                                           int ex, int ey, int phx, int phy, float (&acc)[4], float (&wacc)[4])
+{
+    float R[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) { R[r][0] = pe[r * RWS]; R[r][1] = po[r * RWS]; R[r][2] = pe[r * RWS + 1]; }
+    float Q[2][2][2][2];     // [mask row][mask col][y class][x class]
+#pragma unroll
+    for (int mr = 0; mr < 2; mr++)
+#pragma unroll
+        for (int mc = 0; mc < 2; mc++) {
+            const float2 v0 = q0[mr * MWS + mc], v1 = q1[mr * MWS + mc];
+            Q[mr][mc][0][0] = v0.x; Q[mr][mc][0][1] = v0.y; Q[mr][mc][1][0] = v1.x; Q[mr][mc][1][1] = v1.y;
+        }
+    const int fx[2] = {ex ^ 1, ex}, fy[2] = {ey ^ 1, ey};
+    const int fxy[2][2] = {{fx[0] & fy[0], fx[0] & fy[1]}, {fx[1] & fy[0], fx[1] & fy[1]}};   // [x candidate][y candidate]
+    // G[gy+1][gx+1] = sum over the taps that read raw sample (gx, gy) of weight * certainty.
+    // The 9 taps with px, py in {-2, 0, 2} have one destination each and initialise G; the 16 taps at +-1 are
+    // issued once per candidate destination under the matching predicate (40 predicated FMAs).
+    float G[3][3];
+#pragma unroll
+    for (int py = -2; py <= 2; py += 2)
+#pragma unroll
+        for (int px = -2; px <= 2; px += 2) {
+            const int gy = g_e(0, py), gx = g_e(0, px);
+            G[gy + 1][gx + 1] = w[mt::widx(px, py)] * Q[mt::y_mrow(YM, py)][mt::x_mcol(J, px) - (J >= 2 ? 1 : 0)][gy & 1][gx & 1];
+        }
+#pragma unroll
+    for (int py = -2; py <= 2; py++) {
+#pragma unroll
+        for (int px = -2; px <= 2; px++) {
+            const bool ambx = (px & 1) != 0, amby = (py & 1) != 0;
+            if (!ambx && !amby) continue;
+            const int mr = mt::y_mrow(YM, py), mc = mt::x_mcol(J, px) - (J >= 2 ? 1 : 0);
+            const float wt = w[mt::widx(px, py)];
+#pragma unroll
+            for (int eyc = 0; eyc < (amby ? 2 : 1); eyc++)
+#pragma unroll
+                for (int exc = 0; exc < (ambx ? 2 : 1); exc++) {
+                    const int gy = g_e(eyc, py), gx = g_e(exc, px);
+                    const int flag = (ambx && amby) ? fxy[exc][eyc] : (ambx ? fx[exc] : fy[eyc]);
+                    pfma(G[gy + 1][gx + 1], wt, Q[mr][mc][gy & 1][gx & 1], flag);
+                }
+        }
+    }
+    // class sums (relative to the window centre)
+    float t[4], u[4];
+    t[0] = G[1][1] * R[1][1];                                   u[0] = G[1][1];
+    t[1] = fmaf(G[1][2], R[1][2], G[1][0] * R[1][0]);           u[1] = G[1][0] + G[1][2];
+    t[2] = fmaf(G[2][1], R[2][1], G[0][1] * R[0][1]);           u[2] = G[0][1] + G[2][1];
+    t[3] = fmaf(G[2][2], R[2][2], fmaf(G[2][0], R[2][0], fmaf(G[0][2], R[0][2], G[0][0] * R[0][0])));
+    u[3] = (G[0][0] + G[0][2]) + (G[2][0] + G[2][2]);
+    // route to absolute CFA phase: absolute = relative ^ (phy, phx)
+    {
+        const float t0 = phx ? t[1] : t[0], t1 = phx ? t[0] : t[1], t2 = phx ? t[3] : t[2], t3 = phx ? t[2] : t[3];
+        const float u0 = phx ? u[1] : u[0], u1 = phx ? u[0] : u[1], u2 = phx ? u[3] : u[2], u3 = phx ? u[2] : u[3];
+        acc[0] += phy ? t2 : t0; acc[1] += phy ? t3 : t1; acc[2] += phy ? t0 : t2; acc[3] += phy ? t1 : t3;
+        wacc[0] += phy ? u2 : u0; wacc[1] += phy ? u3 : u1; wacc[2] += phy ? u0 : u2; wacc[3] += phy ? u1 : u3;
+    }
+}
+
+// ---- cold code shared by all 16 (J, YM) variants.  Kept out of line ON PURPOSE: inlined into every variant it is
+// ---- ~350 once-executed instructions per pass (90 KB in total) that stream through the instruction caches and
+// ---- evict the frame loops (profiles/r1e: 23 % of the stall samples on 14 % of the instructions).
+
+// 13 regression weights of absolute HR pixel (X, Y) (:401, :427-430) from the staged kernel-parameter window.
+// kwin: float4 [KHS][KWS], origin (kx0, ky0) in raw coordinates, clamp addressing already applied while staging.
+static __device__ __noinline__ void compute_weights(const float4* __restrict__ kwin, int kws, int kx0, int ky0, int X, int Y, float* __restrict__ wl)
+{
+    const int fx = ((X - 1) >> 1) - kx0, fy = ((Y - 1) >> 1) - ky0;
+    const float4 K00 = kwin[fy * kws + fx], K10 = kwin[fy * kws + fx + 1], K01 = kwin[(fy + 1) * kws + fx], K11 = kwin[(fy + 1) * kws + fx + 1];
+    const float ta = (X & 1) ? 0.25f : 0.75f, tb = (Y & 1) ? 0.25f : 0.75f;
+    const float kx = tex_mix(K00.x, K10.x, K01.x, K11.x, ta, tb);
+    const float ky = tex_mix(K00.y, K10.y, K01.y, K11.y, ta, tb);
+    const float kz = tex_mix(K00.z, K10.z, K01.z, K11.z, ta, tb);
+#pragma unroll
+    for (int py = 0; py <= 2; py++)
+#pragma unroll
+        for (int px = -2; px <= 2; px++) {
+            if (py == 0 && px < 0) continue;
+            const float q = (float)(px * px) * kx + (float)(2 * px * py) * kz + (float)(py * py) * ky;
+            float e;                                     // exp(-q/2) = 2^(-q/2 * log2 e), 2-ulp MUFU
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q * -0.72134752044448170368f));
+            if (!(fabsf(e) < INFINITY)) e = (px * py == 0) ? 1.0f : 0.0f;      // :429-430
+            wl[mt::widx(px, py)] = e;
+        }
+}
+
+// CFA phase -> colour, ApplyWeighting (kernel.cu:426), GammasRGB (:393), one write of one pixel.
+static __device__ __noinline__ void epilogue_px(const FastArgs& F, int x, int y, float a0, float a1, float a2, float a3,
+                                                float b0, float b1, float b2, float b3, float f0, float f1, float f2)
+{
+    const MergeArgs& A = F.a;
+    const float acc[4] = {a0, a1, a2, a3}, wacc[4] = {b0, b1, b2, b3}, fb3[3] = {f0, f1, f2};
+    float s3[3] = {0.f, 0.f, 0.f}, w3[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int col = A.cfa.c[q];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            if (col == c) { s3[c] += acc[q]; w3[c] += wacc[q]; }
+    }
+    if (A.sum_out) {
+        float* so = row_ptr(A.sum_out, A.acc_pitch, y) + 3 * x;
+        float* wo = row_ptr(A.weight_out, A.acc_pitch, y) + 3 * x;
+        so[0] = s3[0]; so[1] = s3[1]; so[2] = s3[2];
+        wo[0] = w3[0]; wo[1] = w3[1]; wo[2] = w3[2];
+    }
+    float* orow = row_ptr(A.out, A.out_pitch, y) + 3 * x;
+#pragma unroll
+    for (int c = 0; c < 3; c++) orow[c] = finish_px(apply_weighting(s3[c], w3[c], fb3[c], A.threshold), A.flags);
+}
+
+// clamped taps, alignment outliers whose window is not staged, outsized shifts (sentinel sx == -128): the reference loop
+static __device__ __noinline__ void slow_pixel(const FastArgs& F, int f, int X, int Y, int sx, int sy, const float* wl, float* ab)
+{
+    if (sx == -128) { const int2 s2 = shift_global(F.a, f, X, Y); sx = s2.x; sy = s2.y; }
+    generic_pixel(F, f, X, Y, sx, sy, wl, ab);
+}
+
+// One pass of one warp: tile row `row` (absolute Y % 4 == YM), the 32 pixels X = X0abs + 4*lane + J.
+template <int TH, int YM, int J>
+__device__ __forceinline__ void run_row(const FastArgs& F, const unsigned char* smem, const int2* fbase, int row, int x0, int y0, int X0abs, int Y0abs)
+{
+    using C = DCfg<TH>;
+    const MergeArgs& A = F.a;
+    const mfsr_merge_geom& g = A.g;
+    const int lane = threadIdx.x & 31;
+    const int y = y0 + row, Y = Y0abs + row;                  // window / absolute row
+    const int x = x0 + 4 * lane + J, X = X0abs + 4 * lane + J;
+    const int N = A.n_frames;
+    if (x < 0 || x >= g.out_w || y < 0 || y >= g.out_h) return;
+    const bool pix_on = x >= 1 && x < g.out_w - 1 && y >= 1 && y < g.out_h - 1;      // the reference skips the window border (:391)
+
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, wacc[4] = {0.f, 0.f, 0.f, 0.f};
+    float fb3[3] = {0.f, 0.f, 0.f};             // ApplyWeighting's inOutImg value, fetched early: its latency hides behind the frame loop
+    if (A.fallback) {
+        const float* p = row_ptr(A.fallback, A.fb_pitch, y) + 3 * x;
+        fb3[0] = __ldg(p); fb3[1] = __ldg(p + 1); fb3[2] = __ldg(p + 2);
+    }
+    if (pix_on) {
+        // ---- regression weights, frame independent (shared out-of-line code; wl doubles as the slow path's copy)
+        float wl[mt::NW], W[mt::NW];
+        compute_weights((const float4*)(smem + (size_t)N * C::FRAME_BYTES), C::KWS, (X0abs >> 1) - 1, (Y0abs >> 1) - 1, X, Y, wl);
+#pragma unroll
+        for (int i = 0; i < mt::NW; i++) W[i] = wl[i];
+        // a pixel-frame runs the staged path when none of its taps (shifted or not) touches the clamp range (:414-419)
+        const int lox = 2 * g.clamp_x0 + 2, spanx = 2 * g.clamp_x1 - 1 - lox, loy = 2 * g.clamp_y0 + 2, spany = 2 * g.clamp_y1 - 1 - loy;
+        const bool pix_stat = spanx >= 0 && spany >= 0 && (unsigned)(Y - loy) <= (unsigned)spany && (unsigned)(X - lox) <= (unsigned)spanx;
+        const int mx0 = (X0abs >> 2) - 1, my0 = (Y0abs >> 2) - 1;
+        // byte offset of the thread's first certainty pixel inside a plane, and of its shift
+        const int mask_off = ((((Y >> 2) + (YM < 2 ? -1 : 0)) - my0) * MWS + (((X >> 2) + (J < 2 ? -1 : 0)) - mx0)) * 8;
+        const unsigned char* shp = smem + (row * TW + 4 * lane + J) * 2;
+        const unsigned char* rawS = smem + C::SHIFT_BYTES;
+        const unsigned char* maskS = smem + C::SHIFT_BYTES + C::RAW_BYTES + mask_off;
+
+#pragma unroll 1
+        for (int f = 0; f < N; f++) {
+            const int2 fb = fbase[f];               // .x = rx0, .y = ry0 of the staged raw window
+            const unsigned sw = *(const unsigned short*)(shp + f * C::FRAME_BYTES);
+            const int sx = bfe_s8(sw, 0), sy = bfe_s8(sw, 8);
+            const int Xs = X + sx, Ys = Y + sy;
+            const int k = Xs >> 1, ky = Ys >> 1;
+            const int cc = k - 1 - fb.x, r0 = ky - 1 - fb.y;              // window column / row of sample (k-1, ky-1)
+            // sentinel sx == -128 marks |shift| > 127 / NaN flow
+            const bool fast = pix_stat && sx != -128 && (unsigned)(Xs - lox) <= (unsigned)spanx && (unsigned)(Ys - loy) <= (unsigned)spany &&
+                              (unsigned)cc <= (unsigned)(RWS - 3) && (unsigned)r0 <= (unsigned)(C::RHS - 3);
+            if (fast) {
+                const int o = cc & 1;
+                const unsigned char* pe = rawS + f * C::FRAME_BYTES + r0 * (RWS * 4) + (cc >> 1) * 4 + o * (RHALF * 4);
+                const unsigned char* po = pe + (o ? 4 - RHALF * 4 : RHALF * 4);
+                const int pl = (k & 1) * 2 + (ky & 1);
+                const unsigned char* q0 = maskS + f * C::FRAME_BYTES + pl * (C::PLANE * 8);
+                const unsigned char* q1 = maskS + f * C::FRAME_BYTES + (pl ^ 1) * (C::PLANE * 8);
+                pixel_fast<J, YM>(W, (const float*)pe, (const float*)po, (const float2*)q0, (const float2*)q1, Xs & 1, Ys & 1, k & 1, ky & 1, acc, wacc);
+            } else {
+                float ab[8];
+                slow_pixel(F, f, X, Y, sx, sy, wl, ab);
+#pragma unroll
+                for (int q = 0; q < 4; q++) { acc[q] += ab[q]; wacc[q] += ab[4 + q]; }
+            }
+        }
+    }
+
+    epilogue_px(F, x, y, acc[0], acc[1], acc[2], acc[3], wacc[0], wacc[1], wacc[2], wacc[3], fb3[0], fb3[1], fb3[2]);
+}
+
+template <int TH, int YM>
+__device__ __forceinline__ void run_rows(const FastArgs& F, const unsigned char* smem, const int2* fbase, int row, int x0, int y0, int X0abs, int Y0abs)
+{
+    run_row<TH, YM, 0>(F, smem, fbase, row, x0, y0, X0abs, Y0abs);
+    run_row<TH, YM, 1>(F, smem, fbase, row, x0, y0, X0abs, Y0abs);
+    run_row<TH, YM, 2>(F, smem, fbase, row, x0, y0, X0abs, Y0abs);
+    run_row<TH, YM, 3>(F, smem, fbase, row, x0, y0, X0abs, Y0abs);
+}
+
+template <int TH>
+__global__ void __launch_bounds__(DCfg<TH>::NT, 512 / DCfg<TH>::NT)
+merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
+{
+    using C = DCfg<TH>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int2 fbase[MAXF];           // origin (rx0, ry0) of the staged raw window per frame
+    __shared__ int s_sum[MAXF][3];         // sum sx, sum sy, count of the tile's (non-outsized) shifts
+    const MergeArgs& A = F.a;
+    const mfsr_merge_geom& g = A.g;
+    const int N = A.n_frames;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = (int)blockIdx.x * TW - F.x_off, y0 = (int)blockIdx.y * TH - F.y_off;   // window coords of the tile origin
+    const int X0abs = x0 + g.org_x, Y0abs = y0 + g.org_y;                                // multiples of 4
+
+    for (int f = tid; f < N; f += C::NT) { s_sum[f][0] = 0; s_sum[f][1] = 0; s_sum[f][2] = 0; }
+    __syncthreads();
+
+    // ---------------- phase 0: integer HR shifts of every tile pixel and frame -> char2 in shared memory
+    {
+        const int Bq = (X0abs >> 2) + lane;
+        const int fxb = 2 * Bq - 1;
+        int cx[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) cx[c] = clampi(fxb + c, 0, g.raw_w - 1);
+        const bool xin = fxb >= 0 && fxb + 3 < g.raw_w;           // the 4 flow columns are contiguous (no clamping)
+        for (int item = warp; item < (TH / 2) * N; item += C::NW_) {
+            const int f = item / (TH / 2), rp = item - f * (TH / 2);
+            const int a = (Y0abs >> 1) + rp;
+            const int ry[3] = {clampi(a - 1, 0, g.raw_h - 1), clampi(a, 0, g.raw_h - 1), clampi(a + 1, 0, g.raw_h - 1)};
+            const float2* flow = (const float2*)((const char*)A.flow + A.flow_fs * f);
+            float2 Fl[3][4];
+            if (xin) {
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    const float2* fr = row_ptr(flow, A.flow_pitch, ry[r]) + fxb;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) Fl[r][c] = __ldg(fr + c);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) Fl[r][c] = __ldg(row_ptr(flow, A.flow_pitch, ry[r]) + cx[c]);
+            }
+            int sum_x = 0, sum_y = 0, cnt = 0;
+            unsigned packed[2][2];
+#pragma unroll
+            for (int yy = 0; yy < 2; yy++) {
+                // even row 2a: flow rows (a-1, a) frac .75 ; odd row 2a+1: rows (a, a+1) frac .25
+                const int rt = yy, rb = yy + 1;
+                const bool ay = (yy == 0);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int c0 = (j + 1) >> 1;
+                    const bool ax = !(j & 1);
+                    const float vx = mix25(mix25(Fl[rt][c0].x, Fl[rt][c0 + 1].x, ax), mix25(Fl[rb][c0].x, Fl[rb][c0 + 1].x, ax), ay);
+                    const float vy = mix25(mix25(Fl[rt][c0].y, Fl[rt][c0 + 1].y, ax), mix25(Fl[rb][c0].y, Fl[rb][c0 + 1].y, ax), ay);
+                    const float rx = roundf(__fmul_rn(vx, 2.0f)), ryf = roundf(__fmul_rn(vy, 2.0f));
+                    const bool big = !(fabsf(rx) <= 127.0f) || !(fabsf(ryf) <= 127.0f);     // NaN / huge: sentinel -128
+                    const int sx = big ? -128 : (int)rx, sy = big ? 0 : (int)ryf;
+                    if (!big) { sum_x += sx; sum_y += sy; cnt++; }
+                    const unsigned v = (unsigned)(sx & 0xff) | ((unsigned)(sy & 0xff) << 8);
+                    if (j & 1) packed[yy][j >> 1] |= v << 16; else packed[yy][j >> 1] = v;
+                }
+            }
+            unsigned char* sh = smem + (size_t)f * C::FRAME_BYTES;
+            *(uint2*)(sh + ((2 * rp) * TW + 4 * lane) * 2) = make_uint2(packed[0][0], packed[0][1]);
+            *(uint2*)(sh + ((2 * rp + 1) * TW + 4 * lane) * 2) = make_uint2(packed[1][0], packed[1][1]);
+            sum_x = __reduce_add_sync(0xffffffffu, sum_x); sum_y = __reduce_add_sync(0xffffffffu, sum_y);
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0) { atomicAdd(&s_sum[f][0], sum_x); atomicAdd(&s_sum[f][1], sum_y); atomicAdd(&s_sum[f][2], cnt); }
+        }
+    }
+    __syncthreads();
+    for (int f = tid; f < N; f += C::NT) {
+        // staged raw window: the tile's own footprint displaced by the MEAN shift, spare rows/columns split evenly
+        const int cnt = max(s_sum[f][2], 1);
+        const int mx = (int)floorf((float)s_sum[f][0] / (float)cnt + 0.5f), my = (int)floorf((float)s_sum[f][1] / (float)cnt + 0.5f);
+        fbase[f] = make_int2((((X0abs + mx - 2) >> 1) - (RWS - (TW / 2 + 3)) / 2) & ~3,
+                             ((Y0abs + my - 2) >> 1) - (C::RHS - (TH / 2 + 3)) / 2);
+    }
+    __syncthreads();
+
+    // ---------------- phase 1: stage normalised raw windows (de-interleaved), the four certainty planes and the
+    // kernel-parameter window; (frame, item) flattened so that every warp instruction carries 32 items
+    {
+        const int mw = g.raw_w / 2, mh = g.raw_h / 2;
+        const int mx0 = (X0abs >> 2) - 1, my0 = (Y0abs >> 2) - 1;
+        constexpr int CH = C::RHS * (RWS / 4);                    // 4-column raw chunks per frame
+        for (int i = tid; i < N * CH; i += C::NT) {
+            const int f = i / CH, ii = i - f * CH;
+            const int r = ii / (RWS / 4), c4 = ii - r * (RWS / 4);
+            const int2 fi = fbase[f];
+            float* rs = (float*)(smem + (size_t)f * C::FRAME_BYTES + C::SHIFT_BYTES);
+            const uint16_t* raw = (const uint16_t*)((const char*)A.raw + A.raw_fs * f);
+            const int yy = clampi(fi.y + r, 0, g.raw_h - 1), xx = fi.x + 4 * c4;
+            const uint16_t* rrow = row_ptr(raw, A.raw_pitch, yy);
+            unsigned v[4];
+            if (xx >= 0 && xx + 3 < g.raw_w) {
+                const uint2 p = __ldg((const uint2*)(rrow + xx));
+                v[0] = p.x & 0xffffu; v[1] = p.x >> 16; v[2] = p.y & 0xffffu; v[3] = p.y >> 16;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) v[k] = __ldg(rrow + clampi(xx + k, 0, g.raw_w - 1));
+            }
+            const int ce = A.cfa.c[(yy & 1) * 2], co = A.cfa.c[(yy & 1) * 2 + 1];       // xx is a multiple of 4
+            const float be = A.black[ce], bo = A.black[co], ie = F.inv_white[ce], io = F.inv_white[co];
+            *(float2*)(rs + r * RWS + 2 * c4) = make_float2(((float)v[0] - be) * ie, ((float)v[2] - be) * ie);
+            *(float2*)(rs + r * RWS + RHALF + 2 * c4) = make_float2(((float)v[1] - bo) * io, ((float)v[3] - bo) * io);
+        }
+        for (int i = tid; i < N * C::PLANE; i += C::NT) {
+            const int f = i / C::PLANE, ii = i - f * C::PLANE;
+            const int r = ii / MWS, c = ii - r * MWS;
+            float2* ms = (float2*)(smem + (size_t)f * C::FRAME_BYTES + C::SHIFT_BYTES + C::RAW_BYTES);
+            const float4* mask = (const float4*)((const char*)A.mask + A.mask_fs * f);
+            const float4 m = __ldg(row_ptr(mask, A.mask_pitch, clampi(my0 + r, 0, mh - 1)) + clampi(mx0 + c, 0, mw - 1));
+            const float ch[3] = {isfinite(m.x) ? m.x : 0.f, isfinite(m.y) ? m.y : 0.f, isfinite(m.z) ? m.z : 0.f};   // :438-439
+            float q4[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) { const int col = A.cfa.c[q]; q4[q] = col == 0 ? ch[0] : (col == 1 ? ch[1] : ch[2]); }
+            // plane = xswap * 2 + absolute y phase; element = (x class 0, x class 1)
+            ms[0 * C::PLANE + ii] = make_float2(q4[0], q4[1]);
+            ms[1 * C::PLANE + ii] = make_float2(q4[2], q4[3]);
+            ms[2 * C::PLANE + ii] = make_float2(q4[1], q4[0]);
+            ms[3 * C::PLANE + ii] = make_float2(q4[3], q4[2]);
+        }
+        // kernel parameters (texture clamp addressing applied here)
+        float4* ks = (float4*)(smem + (size_t)N * C::FRAME_BYTES);
+        const int kx0 = (X0abs >> 1) - 1, ky0 = (Y0abs >> 1) - 1;
+        for (int i = tid; i < C::KWS * C::KHS; i += C::NT) {
+            const int r = i / C::KWS, c = i - r * C::KWS;
+            ks[i] = __ldg(row_ptr(A.kern, A.kern_pitch, clampi(ky0 + r, 0, g.raw_h - 1)) + clampi(kx0 + c, 0, g.raw_w - 1));
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: warp w owns tile row w (Y % 4 == w % 4 == its scheduler): four passes J = 0..3,
+    // each a small loop over the frames (one code variant per warp scheduler at any time)
+    switch (warp & 3) {
+        case 0: run_rows<TH, 0>(F, smem, fbase, warp, x0, y0, X0abs, Y0abs); break;
+        case 1: run_rows<TH, 1>(F, smem, fbase, warp, x0, y0, X0abs, Y0abs); break;
+        case 2: run_rows<TH, 2>(F, smem, fbase, warp, x0, y0, X0abs, Y0abs); break;
+        default: run_rows<TH, 3>(F, smem, fbase, warp, x0, y0, X0abs, Y0abs); break;
+    }
+}
+
+template <int TH>
+int launch_th(const FastArgs& F, cudaStream_t st)
+{
+    using C = DCfg<TH>;
+    const mfsr_merge_geom& g = F.a.g;
+    const size_t smem = (size_t)C::FRAME_BYTES * F.a.n_frames + C::KERN_BYTES;
+    static bool configured = false;
+    if (!configured) {
+        MFSR_CUDA_TRY(cudaFuncSetAttribute(merge_s2_dyn_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    dim3 grid(cdiv(g.out_w + F.x_off, TW), cdiv(g.out_h + F.y_off, TH));
+    merge_s2_dyn_kernel<TH><<<grid, C::NT, smem, st>>>(F);
+    MFSR_LAUNCH_CHECK();
+    return MFSR_OK;
+}
+
+}  // namespace
+
+int launch_merge_s2(const MergeArgs& A, cudaStream_t st)
+{
+    const mfsr_merge_geom& g = A.g;
+    if (g.scale != 2 || A.n_frames < 1 || A.n_frames > MAXF) return MFSR_E_INVALID;
+    if (g.org_x < 0 || g.org_y < 0 || (g.raw_w & 1) || (g.raw_h & 1) || g.raw_w < 8 || g.raw_h < 8) return MFSR_E_INVALID;
+    // vector loads of the staging phase
+    if (((uintptr_t)A.raw & 7) || (A.raw_pitch & 7) || (A.raw_fs & 7)) return MFSR_E_INVALID;
+    if (((uintptr_t)A.mask & 15) || (A.mask_pitch & 15) || (A.mask_fs & 15) || ((uintptr_t)A.kern & 15) || (A.kern_pitch & 15)) return MFSR_E_INVALID;
+    if (((uintptr_t)A.flow & 7) || (A.flow_pitch & 7) || (A.flow_fs & 7)) return MFSR_E_INVALID;
+    FastArgs F;
+    F.a = A;
+    for (int c = 0; c < 3; c++) F.inv_white[c] = 1.0f / A.white[c];
+    F.x_off = g.org_x & 3; F.y_off = g.org_y & 3;
+    static const char* thenv = getenv("MFSR_MERGE_TH");
+    const int want = thenv ? atoi(thenv) : 0;
+    const size_t n = (size_t)A.n_frames, budget1 = 200 * 1024;
+    if (want == 8 && n * DCfg<8>::FRAME_BYTES + DCfg<8>::KERN_BYTES <= budget1) return launch_th<8>(F, st);
+    if (n * DCfg<16>::FRAME_BYTES + DCfg<16>::KERN_BYTES <= budget1) return launch_th<16>(F, st);
+    if (n * DCfg<8>::FRAME_BYTES + DCfg<8>::KERN_BYTES <= budget1) return launch_th<8>(F, st);
+    if (n * DCfg<4>::FRAME_BYTES + DCfg<4>::KERN_BYTES <= budget1) return launch_th<4>(F, st);
+    return MFSR_E_INVALID;
+}
+
+}  // namespace mfsr
