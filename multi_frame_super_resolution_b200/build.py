@@ -23,7 +23,7 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
-    "--expt-relaxed-constexpr",
+    "--expt-relaxed-constexpr", "--extended-lambda",
     "-I", str(ROOT / "include"),
 ]
 

@@ -266,7 +266,7 @@ __device__ __forceinline__ void run_rows(const FastArgs& F, const unsigned char*
 }
 
 template <int TH>
-__global__ void __launch_bounds__(DCfg<TH>::NT, 512 / DCfg<TH>::NT)
+__global__ void __launch_bounds__(DCfg<TH>::NT, DCfg<TH>::NT <= 512 ? 512 / DCfg<TH>::NT : 1)
 merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
 {
     using C = DCfg<TH>;
@@ -283,7 +283,9 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
     for (int f = tid; f < N; f += C::NT) { s_sum[f][0] = 0; s_sum[f][1] = 0; s_sum[f][2] = 0; }
     __syncthreads();
 
-    // ---------------- phase 0: integer HR shifts of every tile pixel and frame -> char2 in shared memory
+    // ---------------- phase 0: integer HR shifts of every tile pixel and frame -> char2 in shared memory.
+    // Work item = (frame, row pair): 8 pixels per lane from a 3 x 4 flow window.  Two items are in flight per warp
+    // (the next window is requested before the current one is consumed) — this phase is pure load latency otherwise.
     {
         const int Bq = (X0abs >> 2) + lane;
         const int fxb = 2 * Bq - 1;
@@ -291,25 +293,25 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
 #pragma unroll
         for (int c = 0; c < 4; c++) cx[c] = clampi(fxb + c, 0, g.raw_w - 1);
         const bool xin = fxb >= 0 && fxb + 3 < g.raw_w;           // the 4 flow columns are contiguous (no clamping)
-        for (int item = warp; item < (TH / 2) * N; item += C::NW_) {
+        const int total = (TH / 2) * N;
+        auto load = [&](int item, float2 (&Fl)[3][4]) {
             const int f = item / (TH / 2), rp = item - f * (TH / 2);
             const int a = (Y0abs >> 1) + rp;
-            const int ry[3] = {clampi(a - 1, 0, g.raw_h - 1), clampi(a, 0, g.raw_h - 1), clampi(a + 1, 0, g.raw_h - 1)};
             const float2* flow = (const float2*)((const char*)A.flow + A.flow_fs * f);
-            float2 Fl[3][4];
-            if (xin) {
 #pragma unroll
-                for (int r = 0; r < 3; r++) {
-                    const float2* fr = row_ptr(flow, A.flow_pitch, ry[r]) + fxb;
+            for (int r = 0; r < 3; r++) {
+                const float2* fr = row_ptr(flow, A.flow_pitch, clampi(a - 1 + r, 0, g.raw_h - 1));
+                if (xin) {
 #pragma unroll
-                    for (int c = 0; c < 4; c++) Fl[r][c] = __ldg(fr + c);
+                    for (int c = 0; c < 4; c++) Fl[r][c] = __ldg(fr + fxb + c);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) Fl[r][c] = __ldg(fr + cx[c]);
                 }
-            } else {
-#pragma unroll
-                for (int r = 0; r < 3; r++)
-#pragma unroll
-                    for (int c = 0; c < 4; c++) Fl[r][c] = __ldg(row_ptr(flow, A.flow_pitch, ry[r]) + cx[c]);
             }
+        };
+        auto emit = [&](int item, const float2 (&Fl)[3][4]) {
+            const int f = item / (TH / 2), rp = item - f * (TH / 2);
             int sum_x = 0, sum_y = 0, cnt = 0;
             unsigned packed[2][2];
 #pragma unroll
@@ -326,7 +328,7 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
                     const float rx = roundf(__fmul_rn(vx, 2.0f)), ryf = roundf(__fmul_rn(vy, 2.0f));
                     const bool big = !(fabsf(rx) <= 127.0f) || !(fabsf(ryf) <= 127.0f);     // NaN / huge: sentinel -128
                     const int sx = big ? -128 : (int)rx, sy = big ? 0 : (int)ryf;
-                    if (!big) { sum_x += sx; sum_y += sy; cnt++; }
+                    if (j == 0 && !big) { sum_x += sx; sum_y += sy; cnt++; }                // mean from a 1-in-4 subsample
                     const unsigned v = (unsigned)(sx & 0xff) | ((unsigned)(sy & 0xff) << 8);
                     if (j & 1) packed[yy][j >> 1] |= v << 16; else packed[yy][j >> 1] = v;
                 }
@@ -337,6 +339,59 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
             sum_x = __reduce_add_sync(0xffffffffu, sum_x); sum_y = __reduce_add_sync(0xffffffffu, sum_y);
             cnt = __reduce_add_sync(0xffffffffu, cnt);
             if (lane == 0) { atomicAdd(&s_sum[f][0], sum_x); atomicAdd(&s_sum[f][1], sum_y); atomicAdd(&s_sum[f][2], cnt); }
+        };
+        float2 FA[3][4], FB[3][4];
+        int item = warp;
+        if (item < total) load(item, FA);
+        while (item < total) {
+            int next = item + C::NW_;
+            if (next < total) load(next, FB);
+            emit(item, FA);
+            item = next;
+            if (item >= total) break;
+            next = item + C::NW_;
+            if (next < total) load(next, FA);
+            emit(item, FB);
+            item = next;
+        }
+    }
+    // ---------------- phase 1a: certainty planes and kernel-parameter window (independent of the shifts)
+    {
+        const int mw = g.raw_w / 2, mh = g.raw_h / 2;
+        const int mx0 = (X0abs >> 2) - 1, my0 = (Y0abs >> 2) - 1;
+        // fixed mask pixel per thread, frames in batches of 4 loads
+        for (int ii = tid; ii < C::PLANE; ii += C::NT) {
+            const int r = ii / MWS, c = ii - r * MWS;
+            float2* ms = (float2*)(smem + C::SHIFT_BYTES + C::RAW_BYTES) + ii;
+            const char* mp = (const char*)A.mask + A.mask_pitch * clampi(my0 + r, 0, mh - 1) + 16 * clampi(mx0 + c, 0, mw - 1);
+            for (int f0 = 0; f0 < N; f0 += 4) {
+                float4 m4[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (f0 + k < N) m4[k] = __ldg((const float4*)(mp + A.mask_fs * (f0 + k)));
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (f0 + k < N) {
+                        const float4 m = m4[k];
+                        const float ch[3] = {isfinite(m.x) ? m.x : 0.f, isfinite(m.y) ? m.y : 0.f, isfinite(m.z) ? m.z : 0.f};   // :438-439
+                        float q4[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) { const int col = A.cfa.c[q]; q4[q] = col == 0 ? ch[0] : (col == 1 ? ch[1] : ch[2]); }
+                        // plane = xswap * 2 + absolute y phase; element = (x class 0, x class 1)
+                        float2* m2 = ms + (size_t)(f0 + k) * (C::FRAME_BYTES / 8);
+                        m2[0 * C::PLANE] = make_float2(q4[0], q4[1]);
+                        m2[1 * C::PLANE] = make_float2(q4[2], q4[3]);
+                        m2[2 * C::PLANE] = make_float2(q4[1], q4[0]);
+                        m2[3 * C::PLANE] = make_float2(q4[3], q4[2]);
+                    }
+            }
+        }
+        // kernel parameters (texture clamp addressing applied here)
+        float4* ks = (float4*)(smem + (size_t)N * C::FRAME_BYTES);
+        const int kx0 = (X0abs >> 1) - 1, ky0 = (Y0abs >> 1) - 1;
+        for (int i = tid; i < C::KWS * C::KHS; i += C::NT) {
+            const int r = i / C::KWS, c = i - r * C::KWS;
+            ks[i] = __ldg(row_ptr(A.kern, A.kern_pitch, clampi(ky0 + r, 0, g.raw_h - 1)) + clampi(kx0 + c, 0, g.raw_w - 1));
         }
     }
     __syncthreads();
@@ -349,55 +404,42 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
     }
     __syncthreads();
 
-    // ---------------- phase 1: stage normalised raw windows (de-interleaved), the four certainty planes and the
-    // kernel-parameter window; (frame, item) flattened so that every warp instruction carries 32 items
+    // ---------------- phase 1b: normalised raw windows (de-interleaved by column parity); a thread owns fixed
+    // 4-column chunks (r, c4) of the window and walks the frames, 4 loads in flight
     {
-        const int mw = g.raw_w / 2, mh = g.raw_h / 2;
-        const int mx0 = (X0abs >> 2) - 1, my0 = (Y0abs >> 2) - 1;
-        constexpr int CH = C::RHS * (RWS / 4);                    // 4-column raw chunks per frame
-        for (int i = tid; i < N * CH; i += C::NT) {
-            const int f = i / CH, ii = i - f * CH;
+        constexpr int CH = C::RHS * (RWS / 4);
+        for (int ii = tid; ii < CH; ii += C::NT) {
             const int r = ii / (RWS / 4), c4 = ii - r * (RWS / 4);
-            const int2 fi = fbase[f];
-            float* rs = (float*)(smem + (size_t)f * C::FRAME_BYTES + C::SHIFT_BYTES);
-            const uint16_t* raw = (const uint16_t*)((const char*)A.raw + A.raw_fs * f);
-            const int yy = clampi(fi.y + r, 0, g.raw_h - 1), xx = fi.x + 4 * c4;
-            const uint16_t* rrow = row_ptr(raw, A.raw_pitch, yy);
-            unsigned v[4];
-            if (xx >= 0 && xx + 3 < g.raw_w) {
-                const uint2 p = __ldg((const uint2*)(rrow + xx));
-                v[0] = p.x & 0xffffu; v[1] = p.x >> 16; v[2] = p.y & 0xffffu; v[3] = p.y >> 16;
-            } else {
+            float* rs0 = (float*)(smem + C::SHIFT_BYTES) + r * RWS + 2 * c4;
+            for (int f0 = 0; f0 < N; f0 += 4) {
+                uint2 p4[4]; int ph4[4]; bool in4[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) v[k] = __ldg(rrow + clampi(xx + k, 0, g.raw_w - 1));
+                for (int k = 0; k < 4; k++)
+                    if (f0 + k < N) {
+                        const int2 fi = fbase[f0 + k];
+                        const int yy = clampi(fi.y + r, 0, g.raw_h - 1), xx = fi.x + 4 * c4;
+                        const uint16_t* rrow = (const uint16_t*)((const char*)A.raw + A.raw_fs * (f0 + k) + A.raw_pitch * yy);
+                        ph4[k] = (yy & 1) * 2;                               // xx is a multiple of 4
+                        in4[k] = xx >= 0 && xx + 3 < g.raw_w;
+                        if (in4[k]) p4[k] = __ldg((const uint2*)(rrow + xx));
+                        else {
+                            unsigned v[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) v[q] = __ldg(rrow + clampi(xx + q, 0, g.raw_w - 1));
+                            p4[k] = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
+                        }
+                    }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (f0 + k < N) {
+                        const uint2 p = p4[k];
+                        const int ph = ph4[k];
+                        const float be = F.black_ph[ph], bo = F.black_ph[ph + 1], ie = F.inv_ph[ph], io = F.inv_ph[ph + 1];
+                        float* rs = rs0 + (size_t)(f0 + k) * (C::FRAME_BYTES / 4);
+                        *(float2*)rs = make_float2(((float)(p.x & 0xffffu) - be) * ie, ((float)(p.y & 0xffffu) - be) * ie);
+                        *(float2*)(rs + RHALF) = make_float2(((float)(p.x >> 16) - bo) * io, ((float)(p.y >> 16) - bo) * io);
+                    }
             }
-            const int ce = A.cfa.c[(yy & 1) * 2], co = A.cfa.c[(yy & 1) * 2 + 1];       // xx is a multiple of 4
-            const float be = A.black[ce], bo = A.black[co], ie = F.inv_white[ce], io = F.inv_white[co];
-            *(float2*)(rs + r * RWS + 2 * c4) = make_float2(((float)v[0] - be) * ie, ((float)v[2] - be) * ie);
-            *(float2*)(rs + r * RWS + RHALF + 2 * c4) = make_float2(((float)v[1] - bo) * io, ((float)v[3] - bo) * io);
-        }
-        for (int i = tid; i < N * C::PLANE; i += C::NT) {
-            const int f = i / C::PLANE, ii = i - f * C::PLANE;
-            const int r = ii / MWS, c = ii - r * MWS;
-            float2* ms = (float2*)(smem + (size_t)f * C::FRAME_BYTES + C::SHIFT_BYTES + C::RAW_BYTES);
-            const float4* mask = (const float4*)((const char*)A.mask + A.mask_fs * f);
-            const float4 m = __ldg(row_ptr(mask, A.mask_pitch, clampi(my0 + r, 0, mh - 1)) + clampi(mx0 + c, 0, mw - 1));
-            const float ch[3] = {isfinite(m.x) ? m.x : 0.f, isfinite(m.y) ? m.y : 0.f, isfinite(m.z) ? m.z : 0.f};   // :438-439
-            float q4[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) { const int col = A.cfa.c[q]; q4[q] = col == 0 ? ch[0] : (col == 1 ? ch[1] : ch[2]); }
-            // plane = xswap * 2 + absolute y phase; element = (x class 0, x class 1)
-            ms[0 * C::PLANE + ii] = make_float2(q4[0], q4[1]);
-            ms[1 * C::PLANE + ii] = make_float2(q4[2], q4[3]);
-            ms[2 * C::PLANE + ii] = make_float2(q4[1], q4[0]);
-            ms[3 * C::PLANE + ii] = make_float2(q4[3], q4[2]);
-        }
-        // kernel parameters (texture clamp addressing applied here)
-        float4* ks = (float4*)(smem + (size_t)N * C::FRAME_BYTES);
-        const int kx0 = (X0abs >> 1) - 1, ky0 = (Y0abs >> 1) - 1;
-        for (int i = tid; i < C::KWS * C::KHS; i += C::NT) {
-            const int r = i / C::KWS, c = i - r * C::KWS;
-            ks[i] = __ldg(row_ptr(A.kern, A.kern_pitch, clampi(ky0 + r, 0, g.raw_h - 1)) + clampi(kx0 + c, 0, g.raw_w - 1));
         }
     }
     __syncthreads();
@@ -443,10 +485,12 @@ int launch_merge_s2(const MergeArgs& A, cudaStream_t st)
     FastArgs F;
     F.a = A;
     for (int c = 0; c < 3; c++) F.inv_white[c] = 1.0f / A.white[c];
+    for (int q = 0; q < 4; q++) { F.black_ph[q] = A.black[A.cfa.c[q]]; F.inv_ph[q] = F.inv_white[A.cfa.c[q]]; }
     F.x_off = g.org_x & 3; F.y_off = g.org_y & 3;
     static const char* thenv = getenv("MFSR_MERGE_TH");
     const int want = thenv ? atoi(thenv) : 0;
     const size_t n = (size_t)A.n_frames, budget1 = 200 * 1024;
+    if (want == 24 && n * DCfg<24>::FRAME_BYTES + DCfg<24>::KERN_BYTES <= budget1) return launch_th<24>(F, st);
     if (want == 8 && n * DCfg<8>::FRAME_BYTES + DCfg<8>::KERN_BYTES <= budget1) return launch_th<8>(F, st);
     if (n * DCfg<16>::FRAME_BYTES + DCfg<16>::KERN_BYTES <= budget1) return launch_th<16>(F, st);
     if (n * DCfg<8>::FRAME_BYTES + DCfg<8>::KERN_BYTES <= budget1) return launch_th<8>(F, st);

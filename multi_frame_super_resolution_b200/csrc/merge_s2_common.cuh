@@ -19,6 +19,7 @@ struct FrameInfo { int rx0, ry0, need_h, slow; };
 struct FastArgs {
     MergeArgs a;
     float inv_white[3];
+    float black_ph[4], inv_ph[4];   // black level / reciprocal white level per CFA phase (y parity * 2 + x parity)
     int x_off, y_off;            // tile grid origin: window x of tile column 0 is -x_off (absolute X multiple of 4)
 };
 
