@@ -36,12 +36,27 @@ constexpr int LTW = 32, LTH = 16, LHW_MAX = 4;
 constexpr int LRW = LTW + 2 * LHW_MAX, LRH = LTH + 2 * LHW_MAX;     // derivative region
 constexpr int LWW = LRW + 4, LWH = LRH + 4;                           // warped / source region
 
-// closed-form 2x2 SVD pseudo-inverse of the window matrix [[a,b],[c,d]] (opticalFlow.cu:236-292),
+// cos / sin of theta = 0.5 * atan2(y, x) without trigonometry (half-angle identities, cancellation-free branch):
+// theta in [-pi/2, pi/2], cos(theta) >= 0, sign(sin(theta)) = sign(y).  Agrees with cosf/sinf(0.5f * atan2f(y, x)) to a few ulp.
+__device__ __forceinline__ void half_angle(float y, float x, float& c, float& s)
+{
+    const float r2 = x * x + y * y;
+    if (!(r2 > 0.0f)) { c = 1.0f; s = 0.0f; if (r2 != r2) { c = r2; s = r2; } return; }     // atan2(0, 0) = 0; NaN propagates
+    const float ir = rsqrtf(r2);
+    const float cx = x * ir;                                   // cos(2 theta)
+    if (x >= 0.0f) { c = sqrtf(0.5f * (1.0f + cx)); s = (0.5f * y * ir) / c; }
+    else           { const float sa = sqrtf(0.5f * (1.0f - cx)); s = copysignf(sa, y); c = (0.5f * fabsf(y) * ir) / sa; }
+}
+
+// closed-form 2x2 SVD pseudo-inverse of the SYMMETRIC window matrix [[a,b],[b,d]] (opticalFlow.cu:236-292 with c == b),
 // including the fminf(sigma1, sigma1) quirk (:255).  Returns false when the reference returns early.
+// For c == b both rotation angles of the reference coincide (theta == eps = 0.5 atan2(2b(a+d), a^2 - d^2)), and their
+// cos/sin come from half_angle() instead of atan2f + cosf + sinf (the kernel was bound by those, ~140 of ~500
+// instructions per pixel).  Singular values, reciprocals, sign fix-ups and the NaN behaviour are kept verbatim.
 __device__ __forceinline__ bool lk_pinv(float a, float b, float c, float d, float minDet, float inv[4])
 {
-    const float theta = 0.5f * atan2f(2.0f * a * c + 2.0f * b * d, a * a + b * b - c * c - d * d);
-    const float ct = cosf(theta), st = sinf(theta);
+    float ct, st;
+    half_angle(2.0f * a * c + 2.0f * b * d, a * a + b * b - c * c - d * d, ct, st);
     const float UT0 = ct, UT2 = -st, UT1 = st, UT3 = ct;
     const float S1 = a * a + b * b + c * c + d * d;
     const float S2 = sqrtf((a * a + b * b - c * c - d * d) * (a * a + b * b - c * c - d * d) + 4 * (a * c + b * d) * (a * c + b * d));
@@ -50,8 +65,7 @@ __device__ __forceinline__ bool lk_pinv(float a, float b, float c, float d, floa
     if (smin < minDet) return false;
     sigma1 = sigma1 != 0 ? 1.0f / sigma1 : 0;
     sigma2 = sigma2 != 0 ? 1.0f / sigma2 : 0;
-    const float eps = 0.5f * atan2f(2.0f * a * b + 2.0f * c * d, a * a - b * b + c * c - d * d);
-    const float ce = cosf(eps), se = sinf(eps);
+    const float ce = ct, se = st;
     float s11 = (a * ct + c * st) * ce + (b * ct + d * st) * se;
     float s22 = (a * st - c * ct) * se + (-b * st + d * ct) * ce;
     s11 = s11 > 0.0f ? 1.0f : s11 < 0 ? -1.0f : 0.0f;
