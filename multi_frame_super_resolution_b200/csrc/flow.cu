@@ -32,9 +32,7 @@ flow_from_tiles_kernel(const float2* __restrict__ tiles, int64_t tile_pitch, int
     row_ptr(flow, flow_pitch, y)[x] = make_float2(sx, sy);
 }
 
-constexpr int LTW = 32, LTH = 16, LHW_MAX = 4;
-constexpr int LRW = LTW + 2 * LHW_MAX, LRH = LTH + 2 * LHW_MAX;     // derivative region
-constexpr int LWW = LRW + 4, LWH = LRH + 4;                           // warped / source region
+constexpr int LTW = 32, LTH = 32, LHW_MAX = 4;          // output tile of one CTA (256 threads)
 
 // cos / sin of theta = 0.5 * atan2(y, x) without trigonometry (half-angle identities, cancellation-free branch):
 // theta in [-pi/2, pi/2], cos(theta) >= 0, sign(sin(theta)) = sign(y).  Agrees with cosf/sinf(0.5f * atan2f(y, x)) to a few ulp.
@@ -78,86 +76,121 @@ __device__ __forceinline__ bool lk_pinv(float a, float b, float c, float d, floa
     return true;
 }
 
-__global__ void __launch_bounds__(256)
+// One LK sweep on a 32x32 tile.  HW (half window) is a template parameter so that every region size, division and
+// loop below is a compile-time constant: the first version (runtime hw, per-element clamped stencils, one output per
+// thread in the window sums) executed 1170 instructions per pixel at 82 % issue utilisation (profiles/r1j_lk_ncu.txt).
+//   W region (source + warped): tile + HW + 2 on each side      R region (derivatives): tile + HW
+template <int HW>
+__global__ void __launch_bounds__(256, 3)
 lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov, int64_t img_pitch,
                     const float2* __restrict__ flow_in, float2* __restrict__ flow_out, int64_t flow_pitch,
-                    int w, int h, int hw, float minDet)
+                    int w, int h, float minDet)
 {
-    __shared__ float s_src[LWH][LWW];
-    __shared__ float s_wrp[LWH][LWW];
-    __shared__ float s_ix[LRH][LRW], s_iy[LRH][LRW], s_it[LRH][LRW];
-    __shared__ float s_h[5][LRH][LTW];
+    constexpr int RW = LTW + 2 * HW, RH = LTH + 2 * HW;       // derivative region
+    constexpr int WW = RW + 4, WH = RH + 4;                   // source / warped region
+    constexpr int NT = 256;
+    // the row sums (step 3) reuse the storage of the source / warped regions, which are dead after step 2
+    constexpr int A_FLOATS = (2 * WH * WW > 5 * RH * LTW) ? 2 * WH * WW : 5 * RH * LTW;
+    __shared__ __align__(16) float s_a[A_FLOATS];
+    __shared__ __align__(16) float s_ix[RH][RW], s_iy[RH][RW], s_it[RH][RW];
+    float (*s_src)[WW] = reinterpret_cast<float (*)[WW]>(s_a);
+    float (*s_wrp)[WW] = reinterpret_cast<float (*)[WW]>(s_a + WH * WW);
+    float (*s_h)[RH][LTW] = reinterpret_cast<float (*)[RH][LTW]>(s_a);
     const int x0 = blockIdx.x * LTW, y0 = blockIdx.y * LTH;
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
-    const int RW = LTW + 2 * hw, RH = LTH + 2 * hw, WW = RW + 4, WH = RH + 4;
-    const int ox = x0 - hw - 2, oy = y0 - hw - 2;         // global coordinate of s_src[0][0]
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int ox = x0 - HW - 2, oy = y0 - HW - 2;             // global coordinate of s_src[0][0]
 
-    // 1. source + warped moved image (WarpingKernel) on the haloed region, clamp addressing
-    for (int i = tid; i < WW * WH; i += nthr) {
+    // 1. source + warped moved image (WarpingKernel, opticalFlow.cu:28) on the haloed region, clamp addressing
+    for (int i = tid; i < WW * WH; i += NT) {
         const int ly = i / WW, lx = i - ly * WW;
         const int gx = clampi(ox + lx, 0, w - 1), gy = clampi(oy + ly, 0, h - 1);
-        s_src[ly][lx] = row_ptr(ref, img_pitch, gy)[gx];
-        const float2 f = row_ptr(flow_in, flow_pitch, gy)[gx];
+        s_src[ly][lx] = __ldg(row_ptr(ref, img_pitch, gy) + gx);
+        const float2 f = __ldg(row_ptr(flow_in, flow_pitch, gy) + gx);
         const TexAxis ax = tex_axis(tex_coord((float)gx + 0.5f + f.x, w, w), w);
         const TexAxis ay = tex_axis(tex_coord((float)gy + 0.5f + f.y, h, h), h);
         const float* r0 = row_ptr(mov, img_pitch, ay.i0);
         const float* r1 = row_ptr(mov, img_pitch, ay.i1);
-        s_wrp[ly][lx] = tex_mix(r0[ax.i0], r0[ax.i1], r1[ax.i0], r1[ax.i1], ax.a, ay.a);
+        s_wrp[ly][lx] = tex_mix(__ldg(r0 + ax.i0), __ldg(r0 + ax.i1), __ldg(r1 + ax.i0), __ldg(r1 + ax.i1), ax.a, ay.a);
     }
     __syncthreads();
-    // 2. derivatives (ComputeDerivativesKernel): 5-tap (1,-8,0,8,-1)/12 on source and warped, clamp
-    for (int i = tid; i < RW * RH; i += nthr) {
+    // 2. derivatives (ComputeDerivativesKernel, :97): 5-tap (1,-8,0,8,-1)/12 on source and warped.  Region elements were
+    // loaded at CLAMPED image coordinates, so plain local neighbours equal the reference's clamp addressing for every
+    // element inside the image; elements outside the image are never read by a valid output (:205-207 skips the border).
+    for (int i = tid; i < RW * RH; i += NT) {
         const int ry = i / RW, rx = i - ry * RW;
-        const int gx = clampi(x0 - hw + rx, 0, w - 1), gy = clampi(y0 - hw + ry, 0, h - 1);
-        const int cy = gy - oy, cx = gx - ox;
-        const int xm2 = clampi(gx - 2, 0, w - 1) - ox, xm1 = clampi(gx - 1, 0, w - 1) - ox;
-        const int xp1 = clampi(gx + 1, 0, w - 1) - ox, xp2 = clampi(gx + 2, 0, w - 1) - ox;
-        const int ym2 = clampi(gy - 2, 0, h - 1) - oy, ym1 = clampi(gy - 1, 0, h - 1) - oy;
-        const int yp1 = clampi(gy + 1, 0, h - 1) - oy, yp2 = clampi(gy + 2, 0, h - 1) - oy;
+        const int cy = ry + 2, cx = rx + 2;
         float t0, t1;
-        t0 = s_src[cy][xp2]; t0 -= s_src[cy][xp1] * 8.0f; t0 += s_src[cy][xm1] * 8.0f; t0 -= s_src[cy][xm2]; t0 /= 12.0f;
-        t1 = s_wrp[cy][xp2]; t1 -= s_wrp[cy][xp1] * 8.0f; t1 += s_wrp[cy][xm1] * 8.0f; t1 -= s_wrp[cy][xm2]; t1 /= 12.0f;
+        t0 = s_src[cy][cx + 2]; t0 -= s_src[cy][cx + 1] * 8.0f; t0 += s_src[cy][cx - 1] * 8.0f; t0 -= s_src[cy][cx - 2]; t0 /= 12.0f;
+        t1 = s_wrp[cy][cx + 2]; t1 -= s_wrp[cy][cx + 1] * 8.0f; t1 += s_wrp[cy][cx - 1] * 8.0f; t1 -= s_wrp[cy][cx - 2]; t1 /= 12.0f;
         s_ix[ry][rx] = (t0 + t1) * 0.5f;
-        // texSource = warped, texTarget = reference: the stencil above is MINUS the derivative, so
-        // Iz = warped - ref is the sign that makes `shift += UV` descend (restated host)
+        // texSource = warped, texTarget = reference: the stencil above is MINUS the derivative, so Iz = warped - ref is
+        // the sign that makes `shift += UV` descend (restated host)
         s_it[ry][rx] = s_wrp[cy][cx] - s_src[cy][cx];
-        t0 = s_src[yp2][cx]; t0 -= s_src[yp1][cx] * 8.0f; t0 += s_src[ym1][cx] * 8.0f; t0 -= s_src[ym2][cx]; t0 /= 12.0f;
-        t1 = s_wrp[yp2][cx]; t1 -= s_wrp[yp1][cx] * 8.0f; t1 += s_wrp[ym1][cx] * 8.0f; t1 -= s_wrp[ym2][cx]; t1 /= 12.0f;
+        t0 = s_src[cy + 2][cx]; t0 -= s_src[cy + 1][cx] * 8.0f; t0 += s_src[cy - 1][cx] * 8.0f; t0 -= s_src[cy - 2][cx]; t0 /= 12.0f;
+        t1 = s_wrp[cy + 2][cx]; t1 -= s_wrp[cy + 1][cx] * 8.0f; t1 += s_wrp[cy - 1][cx] * 8.0f; t1 -= s_wrp[cy - 2][cx]; t1 /= 12.0f;
         s_iy[ry][rx] = (t0 + t1) * 0.5f;
     }
     __syncthreads();
-    // 3. row sums of the five products over [-hw, hw]
-    for (int i = tid; i < LTW * RH; i += nthr) {
-        const int ry = i / LTW, lx = i - ry * LTW;
-        float sxx = 0.f, sxy = 0.f, syy = 0.f, sxt = 0.f, syt = 0.f;
-        for (int k = 0; k <= 2 * hw; k++) {
-            const float dx = s_ix[ry][lx + k], dy = s_iy[ry][lx + k], dt = s_it[ry][lx + k];
-            sxx += dx * dx; sxy += dx * dy; syy += dy * dy; sxt += dx * dt; syt += dy * dt;
+    // 3. row sums of the five products over [-HW, HW]: two adjacent outputs per thread share 2*HW+2 taps (LDS.64)
+    for (int i = tid; i < RH * (LTW / 2); i += NT) {
+        const int ry = i / (LTW / 2), lx = (i - ry * (LTW / 2)) * 2;
+        float dx[2 * HW + 2], dy[2 * HW + 2], dt[2 * HW + 2];
+#pragma unroll
+        for (int k = 0; k < HW + 1; k++) {
+            const float2 a = *(const float2*)&s_ix[ry][lx + 2 * k], b = *(const float2*)&s_iy[ry][lx + 2 * k], c = *(const float2*)&s_it[ry][lx + 2 * k];
+            dx[2 * k] = a.x; dx[2 * k + 1] = a.y; dy[2 * k] = b.x; dy[2 * k + 1] = b.y; dt[2 * k] = c.x; dt[2 * k + 1] = c.y;
         }
-        s_h[0][ry][lx] = sxx; s_h[1][ry][lx] = sxy; s_h[2][ry][lx] = syy; s_h[3][ry][lx] = sxt; s_h[4][ry][lx] = syt;
+#pragma unroll
+        for (int o = 0; o < 2; o++) {
+            float sxx = 0.f, sxy = 0.f, syy = 0.f, sxt = 0.f, syt = 0.f;
+#pragma unroll
+            for (int k = 0; k <= 2 * HW; k++) {
+                sxx += dx[o + k] * dx[o + k]; sxy += dx[o + k] * dy[o + k]; syy += dy[o + k] * dy[o + k];
+                sxt += dx[o + k] * dt[o + k]; syt += dy[o + k] * dt[o + k];
+            }
+            s_h[0][ry][lx + o] = sxx; s_h[1][ry][lx + o] = sxy; s_h[2][ry][lx + o] = syy; s_h[3][ry][lx + o] = sxt; s_h[4][ry][lx + o] = syt;
+        }
     }
     __syncthreads();
-    // 4. column sums, pseudo-inverse, update (lucasKanadeOptim)
-    for (int ly = threadIdx.y; ly < LTH; ly += blockDim.y) {
-        const int lx = threadIdx.x, gx = x0 + lx, gy = y0 + ly;
-        if (gx >= w || gy >= h) continue;
-        float2 f = row_ptr(flow_in, flow_pitch, gy)[gx];
-        if (!(gx < hw || gx >= w - hw || gy < hw || gy >= h - hw)) {
-            float sxx = 0.f, sxy = 0.f, syy = 0.f, sxt = 0.f, syt = 0.f;
-            for (int k = 0; k <= 2 * hw; k++) {
-                sxx += s_h[0][ly + k][lx]; sxy += s_h[1][ly + k][lx]; syy += s_h[2][ly + k][lx];
-                sxt += s_h[3][ly + k][lx]; syt += s_h[4][ly + k][lx];
-            }
-            float inv[4];
-            if (lk_pinv(sxx, sxy, sxy, syy, minDet, inv)) {
-                float u = inv[0] * sxt + inv[1] * syt;
-                float v = inv[2] * sxt + inv[3] * syt;
-                u = isnan(u) ? 0.f : u;
-                v = isnan(v) ? 0.f : v;
-                f.x += u; f.y += v;
+    // 4. column sums, pseudo-inverse, update (lucasKanadeOptim, :190): 4 vertically adjacent pixels per thread
+    {
+        const int lx = threadIdx.x, ly0 = threadIdx.y * 4, gx = x0 + lx;
+        float acc[4][5];
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+#pragma unroll
+            for (int q = 0; q < 5; q++) acc[p][q] = 0.f;
+#pragma unroll
+        for (int r = 0; r < 2 * HW + 4; r++) {
+            float v[5];
+#pragma unroll
+            for (int q = 0; q < 5; q++) v[q] = s_h[q][ly0 + r][lx];
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                if (r >= p && r <= p + 2 * HW) {
+#pragma unroll
+                    for (int q = 0; q < 5; q++) acc[p][q] += v[q];
+                }
+        }
+        if (gx < w) {
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                const int gy = y0 + ly0 + p;
+                if (gy >= h) break;
+                float2 f = __ldg(row_ptr(flow_in, flow_pitch, gy) + gx);
+                if (!(gx < HW || gx >= w - HW || gy < HW || gy >= h - HW)) {
+                    float inv[4];
+                    if (lk_pinv(acc[p][0], acc[p][1], acc[p][1], acc[p][2], minDet, inv)) {
+                        float u = inv[0] * acc[p][3] + inv[1] * acc[p][4];
+                        float v = inv[2] * acc[p][3] + inv[3] * acc[p][4];
+                        u = isnan(u) ? 0.f : u;
+                        v = isnan(v) ? 0.f : v;
+                        f.x += u; f.y += v;
+                    }
+                }
+                row_ptr(flow_out, flow_pitch, gy)[gx] = f;
             }
         }
-        row_ptr(flow_out, flow_pitch, gy)[gx] = f;
     }
 }
 
@@ -184,8 +217,13 @@ extern "C" int mfsr_stage_lk_iteration(const float* ref, const float* mov, int64
     if (!ref || !mov || !flow_in || !flow_out || flow_in == flow_out || width < 1 || height < 1) return MFSR_E_INVALID;
     if (half_window < 1 || half_window > LHW_MAX) return MFSR_E_INVALID;
     dim3 b(LTW, 8), g(cdiv(width, LTW), cdiv(height, LTH));
-    lk_iteration_kernel<<<g, b, 0, (cudaStream_t)stream>>>(ref, mov, img_pitch, (const float2*)flow_in, (float2*)flow_out, flow_pitch,
-                                                          width, height, half_window, min_det);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (half_window) {
+        case 1: lk_iteration_kernel<1><<<g, b, 0, st>>>(ref, mov, img_pitch, (const float2*)flow_in, (float2*)flow_out, flow_pitch, width, height, min_det); break;
+        case 2: lk_iteration_kernel<2><<<g, b, 0, st>>>(ref, mov, img_pitch, (const float2*)flow_in, (float2*)flow_out, flow_pitch, width, height, min_det); break;
+        case 3: lk_iteration_kernel<3><<<g, b, 0, st>>>(ref, mov, img_pitch, (const float2*)flow_in, (float2*)flow_out, flow_pitch, width, height, min_det); break;
+        default: lk_iteration_kernel<4><<<g, b, 0, st>>>(ref, mov, img_pitch, (const float2*)flow_in, (float2*)flow_out, flow_pitch, width, height, min_det); break;
+    }
     MFSR_LAUNCH_CHECK();
     return MFSR_OK;
 }
