@@ -13,11 +13,10 @@ namespace mfsr {
 // CreateFlowFieldFromTiles (opticalFlow.cu:48-93)
 __global__ void __launch_bounds__(256)
 flow_from_tiles_kernel(const float2* __restrict__ tiles, int64_t tile_pitch, int tilesX, int tilesY,
-                       float2* __restrict__ flow, int64_t flow_pitch, int w, int h, float bsx, float bsy, float rot)
+                       float2* __restrict__ flow, int64_t flow_pitch, int w, int h, float bsx, float bsy, float cr, float sr)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
-    const float cr = cosf(rot), sr = sinf(rot);
     float sx = cr * -bsx - sr * -bsy;
     float sy = sr * -bsx + cr * -bsy;
     const float pcx = (float)(x - w / 2), pcy = (float)(y - h / 2);
@@ -206,7 +205,7 @@ extern "C" int mfsr_stage_flow_from_tiles(const float* tile_shift, int64_t tile_
     if (!tile_shift || !flow || tilesX < 1 || tilesY < 1 || width < 1 || height < 1) return MFSR_E_INVALID;
     dim3 b(32, 8), g(cdiv(width, 32), cdiv(height, 8));
     flow_from_tiles_kernel<<<g, b, 0, (cudaStream_t)stream>>>((const float2*)tile_shift, tile_pitch, tilesX, tilesY, (float2*)flow, flow_pitch,
-                                                             width, height, base_shift_x, base_shift_y, base_rotation);
+                                                             width, height, base_shift_x, base_shift_y, cosf(base_rotation), sinf(base_rotation));
     MFSR_LAUNCH_CHECK();
     return MFSR_OK;
 }

@@ -36,7 +36,7 @@ constexpr int RHALF = RWS / 2;   // odd raw columns live RHALF floats after the 
 template <int TH> struct DCfg {
     static constexpr int NW_ = TH;                   // warps: one per tile row
     static constexpr int NT = 32 * TH;               // threads
-    static constexpr int RHS = TH / 2 + 7;           // staged raw rows (TH/2 + taps 3 + slack 4)
+    static constexpr int RHS = TH / 2 + 15;          // staged raw rows (TH/2 + taps 3 + shift slack +-6 raw rows)
     static constexpr int MHS = TH / 4 + 2;           // staged certainty rows
     static constexpr int PLANE = MHS * MWS;          // float2 elements per certainty plane
     static constexpr int SHIFT_BYTES = TH * TW * 2;
@@ -65,16 +65,13 @@ __device__ __forceinline__ int bfe_s8(unsigned v, int pos)
 // One pixel, one frame, everything in shared memory.  J = X % 4 and YM = Y % 4 are static; the parities of
 // X+sx / Y+sy (ex, ey) are lane predicates; the CFA phase of the window centre only moves addresses (pe/po,
 // q0/q1) and the final routing (phx, phy).
-//   pe : staged raw sample (ky-1, k-1); (ky-1, k+1) is the next float (de-interleaved rows)   po : (ky-1, k)
+//   R  : normalised raw samples R[gy+1][gx+1] around (k, ky)
 //   q0 / q1 : certainty planes of y class 0 / 1 at the thread's first mask pixel
 template <int J, int YM>
-__device__ __forceinline__ void pixel_fast(const float (&w)[mt::NW], const float* __restrict__ pe, const float* __restrict__ po,
+__device__ __forceinline__ void pixel_fast(const float (&w)[mt::NW], const float (&R)[3][3],
                                            const float2* __restrict__ q0, const float2* __restrict__ q1,
                                            int ex, int ey, int phx, int phy, float (&acc)[4], float (&wacc)[4])
 {
-    float R[3][3];
-#pragma unroll
-    for (int r = 0; r < 3; r++) { R[r][0] = pe[r * RWS]; R[r][1] = po[r * RWS]; R[r][2] = pe[r * RWS + 1]; }
     float Q[2][2][2][2];     // [mask row][mask col][y class][x class]
 #pragma unroll
     for (int mr = 0; mr < 2; mr++)
@@ -182,7 +179,29 @@ static __device__ __noinline__ void epilogue_px(const FastArgs& F, int x, int y,
     for (int c = 0; c < 3; c++) orow[c] = finish_px(apply_weighting(s3[c], w3[c], fb3[c], A.threshold), A.flags);
 }
 
-// clamped taps, alignment outliers whose window is not staged, outsized shifts (sentinel sx == -128): the reference loop
+// 3x3 normalised raw samples around (k, ky) of an alignment outlier whose window is not staged, from global memory.
+// No clamping: the caller has checked that every tap stays inside the clamp range.
+static __device__ __noinline__ void fetch_raw_global(const FastArgs& F, int f, int k, int ky, float* __restrict__ out9)
+{
+    const MergeArgs& A = F.a;
+    const uint16_t* raw = (const uint16_t*)((const char*)A.raw + A.raw_fs * f);
+    unsigned v[9];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        const uint16_t* rrow = row_ptr(raw, A.raw_pitch, ky - 1 + r) + (k - 1);
+#pragma unroll
+        for (int c = 0; c < 3; c++) v[r * 3 + c] = __ldg(rrow + c);
+    }
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const int ph = ((ky - 1 + r) & 1) * 2 + ((k - 1 + c) & 1);
+            out9[r * 3 + c] = ((float)v[r * 3 + c] - F.black_ph[ph]) * F.inv_ph[ph];
+        }
+}
+
+// clamped taps and outsized shifts (sentinel sx == -128): the reference loop
 static __device__ __noinline__ void slow_pixel(const FastArgs& F, int f, int X, int Y, int sx, int sy, const float* wl, float* ab)
 {
     if (sx == -128) { const int2 s2 = shift_global(F.a, f, X, Y); sx = s2.x; sy = s2.y; }
@@ -234,16 +253,25 @@ __device__ __forceinline__ void run_row(const FastArgs& F, const unsigned char* 
             const int k = Xs >> 1, ky = Ys >> 1;
             const int cc = k - 1 - fb.x, r0 = ky - 1 - fb.y;              // window column / row of sample (k-1, ky-1)
             // sentinel sx == -128 marks |shift| > 127 / NaN flow
-            const bool fast = pix_stat && sx != -128 && (unsigned)(Xs - lox) <= (unsigned)spanx && (unsigned)(Ys - loy) <= (unsigned)spany &&
-                              (unsigned)cc <= (unsigned)(RWS - 3) && (unsigned)r0 <= (unsigned)(C::RHS - 3);
-            if (fast) {
-                const int o = cc & 1;
-                const unsigned char* pe = rawS + f * C::FRAME_BYTES + r0 * (RWS * 4) + (cc >> 1) * 4 + o * (RHALF * 4);
-                const unsigned char* po = pe + (o ? 4 - RHALF * 4 : RHALF * 4);
+            const bool noclamp = pix_stat && sx != -128 && (unsigned)(Xs - lox) <= (unsigned)spanx && (unsigned)(Ys - loy) <= (unsigned)spany;
+            if (noclamp) {
+                float R[3][3];
+                if ((unsigned)cc <= (unsigned)(RWS - 3) && (unsigned)r0 <= (unsigned)(C::RHS - 3)) {
+                    const int o = cc & 1;
+                    const float* pe = (const float*)(rawS + f * C::FRAME_BYTES + r0 * (RWS * 4) + (cc >> 1) * 4 + o * (RHALF * 4));
+                    const float* po = pe + (o ? 1 - RHALF : RHALF);
+#pragma unroll
+                    for (int r = 0; r < 3; r++) { R[r][0] = pe[r * RWS]; R[r][1] = po[r * RWS]; R[r][2] = pe[r * RWS + 1]; }
+                } else {                                   // alignment outlier: its window is not staged
+                    float tmp[9];
+                    fetch_raw_global(F, f, k, ky, tmp);
+#pragma unroll
+                    for (int r = 0; r < 3; r++) { R[r][0] = tmp[3 * r]; R[r][1] = tmp[3 * r + 1]; R[r][2] = tmp[3 * r + 2]; }
+                }
                 const int pl = (k & 1) * 2 + (ky & 1);
                 const unsigned char* q0 = maskS + f * C::FRAME_BYTES + pl * (C::PLANE * 8);
                 const unsigned char* q1 = maskS + f * C::FRAME_BYTES + (pl ^ 1) * (C::PLANE * 8);
-                pixel_fast<J, YM>(W, (const float*)pe, (const float*)po, (const float2*)q0, (const float2*)q1, Xs & 1, Ys & 1, k & 1, ky & 1, acc, wacc);
+                pixel_fast<J, YM>(W, R, (const float2*)q0, (const float2*)q1, Xs & 1, Ys & 1, k & 1, ky & 1, acc, wacc);
             } else {
                 float ab[8];
                 slow_pixel(F, f, X, Y, sx, sy, wl, ab);

@@ -10,7 +10,7 @@ namespace mfsr {
 namespace s2 {
 
 constexpr int TW = 128;          // output tile width
-constexpr int RWS = 80;          // staged raw window: columns (64 + taps + alignment + shift slack)
+constexpr int RWS = 96;          // staged raw window: columns (64 + taps 3 + alignment 3 + shift slack +-13 raw px)
 constexpr int MWS = 34;          // staged certainty window: columns (TW/4 + 2)
 constexpr int MAXF = 40;         // frames the shared-memory bookkeeping is sized for
 

@@ -1,8 +1,11 @@
 """Seeded synthetic bursts: an analytic scene rendered at sub-pixel offsets.
 
-Scene = sum of random sinusoids (area-sampled exactly: amplitude x sinc of the pixel
-aperture, so frequencies above the LR Nyquist alias the way a real sensor aliases) +
-soft straight edges + a slow colour tint; per-frame motion = global translation U(-a,a)
+Scene = multi-octave value-noise texture (non-periodic, ~1/f spectrum like natural images:
+block matching has one minimum) + random sinusoids (area-sampled exactly: amplitude x sinc
+of the pixel aperture, so frequencies above the LR Nyquist alias the way a real sensor
+aliases) + soft straight edges + a slow colour tint.  A scene made of global plane waves
+alone is self-similar under translation and makes the tile matcher lock onto wrong periods
+for some seeds (tools/flow_stats2.py), which no camera scene does; per-frame motion = global translation U(-a,a)
 plus a long-wavelength warp; noise sigma^2 = alpha*I + beta; 10-bit quantisation in a u16
 container (black 64, white 1023); RGGB mosaic or gray.  Runs on CPU (tests) or CUDA (bench)
 with identical code; there is no network, so this replaces real captures.
@@ -38,6 +41,15 @@ def synth_burst(n_frames: int, height: int, width: int, seed: int = 1234, device
     shifts = (rnd(n_frames, 2) * 2 - 1) * max_shift
     shifts[0] = 0
     wph = rnd(n_frames, 2) * 2 * math.pi
+    # value-noise octaves: cell size 192 .. 3 LR pixels, amplitude ~ sqrt(cell) (1/f-like), bilinear evaluation
+    octaves = []
+    cell = 192.0
+    while cell >= 3.0:
+        gw, gh = int(width / cell) + 3, int(height / cell) + 3
+        grid = torch.rand((1, 1, gh, gw), generator=g, dtype=torch.float32) * 2 - 1
+        octaves.append((cell, grid.to(device), math.sqrt(cell / 192.0)))
+        cell /= 2.0
+    onorm = math.sqrt(sum(a * a for _, _, a in octaves))
 
     ys = torch.arange(height, device=dev, dtype=torch.float32).view(-1, 1)
     xs = torch.arange(width, device=dev, dtype=torch.float32).view(1, -1)
@@ -53,7 +65,16 @@ def synth_burst(n_frames: int, height: int, width: int, seed: int = 1234, device
         acc = torch.zeros_like(img)
         for k in range(n_sines):
             acc += float(amp[k]) * torch.sin(2 * math.pi * (float(fx[k]) * X + float(fy[k]) * Y) + float(ph[k]))
-        img += 0.25 * acc / math.sqrt(n_sines / 8.0)
+        img += 0.10 * acc / math.sqrt(n_sines / 8.0)
+        tex = torch.zeros_like(img)
+        for cell, grid, a in octaves:
+            gh, gw = grid.shape[-2:]
+            # grid node i sits at LR coordinate (i - 1) * cell; align_corners=True maps [-1, 1] onto nodes 0 .. n-1
+            u = ((X / cell + 1.0) / (gw - 1)) * 2 - 1
+            v = ((Y / cell + 1.0) / (gh - 1)) * 2 - 1
+            tex += a * torch.nn.functional.grid_sample(grid, torch.stack([u, v], dim=-1).unsqueeze(0), mode="bilinear",
+                                                       padding_mode="border", align_corners=True)[0, 0]
+        img += 0.22 * tex / onorm
         for k in range(n_edges):
             d = math.cos(float(en[k])) * X + math.sin(float(en[k])) * Y - float(eo[k]) * diag
             img += float(ec[k]) * torch.sigmoid(d / 0.35)
