@@ -44,9 +44,9 @@ __device__ __forceinline__ void tile_disp(const TileAlignArgs& A, int tix, int t
     dx = (int)roundf(sx); dy = (int)roundf(sy);
 }
 
-// One block per (tile, pair).  Dynamic smem: mov patch P rows x PW words, ref patch T rows x T/4 words, S*S floats.
+// Generic tile sizes: one block per (tile, pair).  Dynamic smem: mov patch P rows x PW words, ref patch T rows x T/4 words, S*S floats.
 __global__ void __launch_bounds__(96)
-tile_align_kernel(const __grid_constant__ TileAlignArgs AA)
+tile_align_generic_kernel(const __grid_constant__ TileAlignArgs AA)
 {
     extern __shared__ uint32_t smem[];
     const TileAlignArgs& A = AA;
@@ -178,6 +178,211 @@ tile_align_kernel(const __grid_constant__ TileAlignArgs AA)
             row_ptr(outp, B.out_pitch, tiy)[tix] = make_float2(cx + (float)(dxm - dxr), cy + (float)(dym - dyr));
         }
     }
+}
+
+// findMinimum (kernel.cu:512-636) by one warp on an S x S SSD map in shared memory: (value, index) arg-min with strict
+// '<' so that the lowest linear index wins ties, 3x3 quadratic sub-pixel fit by lane 0.  Writes the tile's shift.
+__device__ __forceinline__ void find_minimum_warp(const float* s_ssd, int S, int M, int lane, float threshold, int2* argminp, int t,
+                                                  float2* outp, int64_t out_pitch, int tix, int tiy, float addx, float addy)
+{
+    const int nlag = S * S;
+    float minVal = FLT_MAX, maxVal = -FLT_MAX; int minIdx = -1;
+    for (int i = lane; i < nlag; i += 32) {
+        const float v = s_ssd[i];
+        maxVal = fmaxf(maxVal, v);
+        if (v < minVal) { minVal = v; minIdx = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, minVal, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, minIdx, o);
+        const float om = __shfl_xor_sync(0xffffffffu, maxVal, o);
+        maxVal = fmaxf(maxVal, om);
+        if (oi >= 0 && (ov < minVal || (ov == minVal && (minIdx < 0 || oi < minIdx)))) { minVal = ov; minIdx = oi; }
+    }
+    if (lane == 0) {
+        float cy = (float)(minIdx / S);
+        float cx = (float)minIdx - cy * (float)S;
+        if (argminp) argminp[t] = make_int2((int)cx - M, (int)cy - M);
+        if (cx < 1 || cy < 1 || cx >= 2 * M || cy >= 2 * M) { cx = 0; cy = 0; }
+        else {
+            float A11 = 0, A22 = 0, A12 = 0, b1 = 0, b2 = 0;
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+                const int off = (i < 3) ? (i - 1 - S) : (i < 6 ? i - 4 : i - 7 + S);
+                const float g = s_ssd[minIdx + off];
+                A11 += c_FA11[i] * g; A22 += c_FA22[i] * g; A12 += c_FA12[i] * g; b1 += c_Fb1[i] * g; b2 += c_Fb2[i] * g;
+            }
+            A11 = fmaxf(A11, 0.0f); A22 = fmaxf(A22, 0.0f);
+            float det = A11 * A22 - A12 * A12;
+            if (det < 0) { A12 = 0; det = A11 * A22; }
+            if (det != 0) {
+                float muX = (A22 * b1 - A12 * b2) / det;
+                float muY = (A11 * b2 - A12 * b1) / det;
+                if (fabsf(muX) > 1) muX = 0;
+                if (fabsf(muY) > 1) muY = 0;
+                cx -= muX; cy -= muY;
+            }
+            cx -= M; cy -= M;
+        }
+        if (threshold + minVal > maxVal) { cx = 0; cy = 0; }
+        row_ptr(outp, out_pitch, tiy)[tix] = make_float2(cx + addx, cy + addy);
+    }
+}
+
+// Correlation of one lane's group of up to 4 horizontally adjacent lags (lx = 4g .. 4g+3, one ly) for T = 16.
+// AL = byte alignment of the moved patch inside its aligned words (warp-uniform): window word offsets and funnel
+// shifts are compile-time, the 6 moved words of a row serve all 4 lags.
+template <int AL>
+__device__ __forceinline__ void cc_group16(const uint32_t* __restrict__ mov, int pwa, const uint32_t* __restrict__ ref, unsigned (&cc)[4])
+{
+#pragma unroll 4
+    for (int y = 0; y < 16; y++) {
+        uint32_t W[6], R[4];
+#pragma unroll
+        for (int k = 0; k < 6; k++) W[k] = mov[y * pwa + k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) R[k] = ref[y * 4 + k];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int o = (AL + j) >> 2, sh = ((AL + j) & 3) * 8;
+#pragma unroll
+            for (int xw = 0; xw < 4; xw++) {
+                const uint32_t iv = sh ? __funnelshift_r(W[xw + o], W[xw + o + 1], sh) : W[xw + o];
+                cc[j] = __dp4a(R[xw], iv, cc[j]);
+            }
+        }
+    }
+}
+
+// T = 16 fast path: ONE WARP per (tile, pair), four per block, no block barriers.
+//  * patches are fetched as aligned 32-bit words (the byte-gather version issued ~930 u8 loads per tile and pair),
+//    the moved patch keeps its alignment and is funnel-shifted at use;
+//  * the window energy sum I^2 comes from row sums + a column prefix (exact integers, any order) instead of a second
+//    dp4a per lag and word;
+//  * a lane computes 4 adjacent lags from one set of loaded words.
+__global__ void __launch_bounds__(128)
+tile_align16_kernel(const __grid_constant__ TileAlignArgs AA)
+{
+    extern __shared__ uint32_t smem[];
+    const TileAlignArgs& A = AA;
+    const TileAlignBatch& B = A.b;
+    constexpr int T = 16, TW = 4;
+    const int M = B.M, P = T + 2 * M, S = 2 * M + 1, nlag = S * S;
+    const int PWA = (P + 6) / 4 + 1;
+    const int per_warp = P * PWA + T * TW + (P + 1) * S + nlag;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 4 + warp, pair = blockIdx.y;
+    if (t >= B.tx * B.ty) return;
+    uint32_t* s_mov = smem + warp * per_warp;             // [P][PWA] aligned words
+    uint32_t* s_ref = s_mov + P * PWA;                    // [T][TW] exact patch words
+    int* s_cp = (int*)(s_ref + T * TW);                   // [P + 1][S] column prefix of the row window energies
+    float* s_ssd = (float*)(s_cp + (P + 1) * S);          // [nlag]
+    const uint8_t* img_ref = B.img + B.frame_stride * (int64_t)B.pt.from[pair];
+    const uint8_t* img_mov = B.img + B.frame_stride * (int64_t)B.pt.to[pair];
+    const float2* pre = B.pre ? (const float2*)((const char*)B.pre + B.pre_pair_stride * pair) : nullptr;
+    float2* outp = (float2*)((char*)B.out + B.out_pair_stride * pair);
+    int2* argminp = B.argmin ? (int2*)((char*)B.argmin + B.argmin_pair_stride * pair) : nullptr;
+    float* ssdp = B.ssd ? (float*)((char*)B.ssd + B.ssd_pair_stride * pair) : nullptr;
+    const int tiy = t / B.tx, tix = t - tiy * B.tx;
+
+    float prex = 0.f, prey = 0.f;
+    if (pre) { const float2 p = row_ptr(pre, B.pre_pitch, tiy)[tix]; prex = p.x; prey = p.y; }
+    int dxm, dym, dxr, dyr;
+    tile_disp(A, tix, tiy, prex, prey, dxm, dym);
+    tile_disp(A, tix, tiy, 0.f, 0.f, dxr, dyr);
+
+    // ---- moved patch (clamped like kernel.cu:371-372)
+    const int gxs = tix * T + dxm, gys = tiy * T + dym;
+    const bool mfast = gxs >= 0 && gxs + P <= B.w && (int64_t)((gxs & ~3) + 4 * PWA) <= B.pitch;
+    const int al = mfast ? (gxs & 3) : 0;
+    if (mfast) {
+        const int xa = gxs & ~3;
+        for (int i = lane; i < P * PWA; i += 32) {
+            const int py = i / PWA, k = i - py * PWA;
+            s_mov[i] = __ldg((const uint32_t*)(row_ptr(img_mov, B.pitch, clampi(gys + py, 0, B.h - 1)) + xa) + k);
+        }
+    } else {
+        for (int i = lane; i < P * PWA; i += 32) {
+            const int py = i / PWA, k = i - py * PWA;
+            const uint8_t* row = row_ptr(img_mov, B.pitch, clampi(gys + py, 0, B.h - 1));
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int px = k * 4 + b;
+                v |= (px < P ? (uint32_t)row[clampi(gxs + px, 0, B.w - 1)] : 0u) << (8 * b);
+            }
+            s_mov[i] = v;
+        }
+    }
+    // ---- template patch (kernel.cu:312-313), exact alignment
+    const int gxr = tix * T + M + dxr, gyr = tiy * T + M + dyr;
+    const bool rfast = gxr >= 0 && gxr + T <= B.w && (int64_t)((gxr & ~3) + T + 4) <= B.pitch;
+    for (int i = lane; i < T * TW; i += 32) {
+        const int py = i >> 2, xw = i & 3;
+        const uint8_t* row = row_ptr(img_ref, B.pitch, clampi(gyr + py, 0, B.h - 1));
+        uint32_t v;
+        if (rfast) {
+            const uint32_t* wp = (const uint32_t*)(row + (gxr & ~3)) + xw;
+            const int sh = (gxr & 3) * 8;
+            const uint32_t w0 = __ldg(wp);
+            v = sh ? __funnelshift_r(w0, __ldg(wp + 1), sh) : w0;
+        } else {
+            v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) v |= (uint32_t)row[clampi(gxr + xw * 4 + b, 0, B.w - 1)] << (8 * b);
+        }
+        s_ref[i] = v;
+    }
+    __syncwarp();
+    // ---- sum of squares of the template (squaredSum, kernel.cu:119)
+    unsigned sumT2 = 0;
+    for (int i = lane; i < T * TW; i += 32) sumT2 = __dp4a(s_ref[i], s_ref[i], sumT2);
+    for (int o = 16; o > 0; o >>= 1) sumT2 += __shfl_xor_sync(0xffffffffu, sumT2, o);
+    // ---- window energies (boxFilterWithBorderX/Y of I^2, kernel.cu:149,:186): row sums, then column prefix
+    for (int i = lane; i < P * S; i += 32) {
+        const int y = i / S, lx = i - y * S;
+        const int b = al + lx, wq = b >> 2, sh = (b & 3) * 8;
+        const uint32_t* mr = s_mov + y * PWA + wq;
+        unsigned e = 0;
+#pragma unroll
+        for (int xw = 0; xw < TW; xw++) {
+            const uint32_t iv = __funnelshift_r(mr[xw], mr[xw + 1], sh);
+            e = __dp4a(iv, iv, e);
+        }
+        s_cp[(y + 1) * S + lx] = (int)e;
+    }
+    __syncwarp();
+    if (lane < S) {
+        int run = 0;
+        s_cp[lane] = 0;
+        for (int y = 1; y <= P; y++) { run += s_cp[y * S + lane]; s_cp[y * S + lane] = run; }
+    }
+    __syncwarp();
+    // ---- correlation + SSD map (normalizedCC, kernel.cu:227): SSD = sumT2 + sumI2 - 2 CC, exact in int32
+    const int NG = (S + 3) / 4;
+    for (int it = lane; it < S * NG; it += 32) {
+        const int ly = it / NG, g = it - ly * NG;
+        unsigned cc[4] = {0u, 0u, 0u, 0u};
+        const uint32_t* mv = s_mov + ly * PWA + g;
+        switch (al) {
+            case 0: cc_group16<0>(mv, PWA, s_ref, cc); break;
+            case 1: cc_group16<1>(mv, PWA, s_ref, cc); break;
+            case 2: cc_group16<2>(mv, PWA, s_ref, cc); break;
+            default: cc_group16<3>(mv, PWA, s_ref, cc); break;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int lx = 4 * g + j;
+            if (lx < S) {
+                const int i2 = s_cp[(ly + T) * S + lx] - s_cp[ly * S + lx];
+                const float v = (float)((int)(sumT2 + (unsigned)i2) - 2 * (int)cc[j]);
+                s_ssd[ly * S + lx] = v;
+                if (ssdp) ssdp[(size_t)t * nlag + ly * S + lx] = v;
+            }
+        }
+    }
+    __syncwarp();
+    find_minimum_warp(s_ssd, S, M, lane, B.threshold, argminp, t, outp, B.out_pitch, tix, tiy, (float)(dxm - dxr), (float)(dym - dyr));
 }
 
 // UpSampleShifts (kernel.cu:642-688)
@@ -322,9 +527,19 @@ int mfsr::launch_tile_align(const TileAlignBatch& b, cudaStream_t st)
     TileAlignArgs A;
     A.b = b; A.sf = sinf(b.rot); A.cf = cosf(b.rot);
     const int P = b.T + 2 * b.M, S = 2 * b.M + 1, PW = (P + 3) / 4 + 1;
+    // T = 16 with word-aligned images: warp-per-tile kernel
+    if (b.T == 16 && !(((uintptr_t)b.img | (uintptr_t)b.pitch | (uintptr_t)b.frame_stride) & 3)) {
+        const int PWA = (P + 6) / 4 + 1;
+        const size_t smem16 = (size_t)4 * (P * PWA + 16 * 4 + (P + 1) * S + S * S) * 4;
+        if (smem16 <= 48 * 1024) {
+            tile_align16_kernel<<<dim3(cdiv(b.tx * b.ty, 4), b.n_pairs), 128, smem16, st>>>(A);
+            MFSR_LAUNCH_CHECK();
+            return MFSR_OK;
+        }
+    }
     const size_t smem = (size_t)(P * PW + b.T * (b.T / 4)) * 4 + (size_t)S * S * 4;
     if (smem > 48 * 1024) return MFSR_E_INVALID;
-    tile_align_kernel<<<dim3(b.tx * b.ty, b.n_pairs), 96, smem, st>>>(A);
+    tile_align_generic_kernel<<<dim3(b.tx * b.ty, b.n_pairs), 96, smem, st>>>(A);
     MFSR_LAUNCH_CHECK();
     return MFSR_OK;
 }
