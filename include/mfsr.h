@@ -297,6 +297,10 @@ int mfsr_set_frames(mfsr_handle h, const void* const* frames, int n, int width, 
  * (out_w x out_h), device pointer, or host pointer when out_on_host != 0
  * (copied D2H and synchronised).  Device output is NOT synchronised. */
 int mfsr_run(mfsr_handle h, float* out, int64_t out_pitch, int out_on_host);
+/* Same, but never synchronises: with a (pinned) host `out` the D2H copy is only enqueued; call
+ * mfsr_synchronize(h) before reading it or re-using the handle's frames.  Two handles driven alternately
+ * overlap one burst's PCIe transfers with the other's kernels (the way bench.py measures `e2e`). */
+int mfsr_run_async(mfsr_handle h, float* out, int64_t out_pitch, int out_on_host);
 int mfsr_synchronize(mfsr_handle h);
 void* mfsr_stream(mfsr_handle h);
 

@@ -271,7 +271,12 @@ extern "C" int mfsr_set_frames(mfsr_handle h, const void* const* frames, int n, 
 
 #define RUN(expr) do { int _rc = (expr); if (_rc) return _rc; h->launches++; } while (0)
 
-extern "C" int mfsr_run(mfsr_handle h, float* out, int64_t out_pitch, int out_on_host)
+static int run_impl(mfsr_handle h, float* out, int64_t out_pitch, int out_on_host, bool sync_host);
+
+extern "C" int mfsr_run(mfsr_handle h, float* out, int64_t out_pitch, int out_on_host) { return run_impl(h, out, out_pitch, out_on_host, true); }
+extern "C" int mfsr_run_async(mfsr_handle h, float* out, int64_t out_pitch, int out_on_host) { return run_impl(h, out, out_pitch, out_on_host, false); }
+
+static int run_impl(mfsr_handle h, float* out, int64_t out_pitch, int out_on_host, bool sync_host)
 {
     if (!h || !out) return MFSR_E_INVALID;
     if (!h->have_frames) return MFSR_E_STATE;
@@ -386,7 +391,7 @@ extern "C" int mfsr_run(mfsr_handle h, float* out, int64_t out_pitch, int out_on
         MFSR_CUDA_TRY(cudaMemcpy2DAsync(out, out_pitch, h->outbuf, h->out_pitch_own, (size_t)h->geom.out_w * 12, h->geom.out_h, cudaMemcpyDeviceToHost, st));
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_COUNT], st));
     h->ran = true;
-    if (out_on_host) MFSR_CUDA_TRY(cudaStreamSynchronize(st));
+    if (out_on_host && sync_host) MFSR_CUDA_TRY(cudaStreamSynchronize(st));
     return MFSR_OK;
 }
 

@@ -136,7 +136,8 @@ class BurstSuperResolution:
         self._keep = frames          # the async H2D copies read it until the stream reaches them
 
     # -- nextFrame: run the whole chain, return the float3 image
-    def next_frame(self, out=None, host: bool = False):
+    def next_frame(self, out=None, host: bool = False, sync: bool = True):
+        """host=True: `out` is host memory; sync=False only enqueues the D2H copy (pinned `out`), call synchronize()."""
         if self._shape is None:
             raise RuntimeError("set_input() first")
         ow, oh = self.output_size(self._shape[1], self._shape[0])
@@ -144,7 +145,9 @@ class BurstSuperResolution:
             if out is None:
                 out = torch.empty((oh, ow, 3), dtype=torch.float32, pin_memory=True)
             ptr = out.data_ptr() if isinstance(out, torch.Tensor) else out.ctypes.data
-            check(self._lib.mfsr_run(self._h, C.c_void_p(ptr), ow * 12, 1), "mfsr_run")
+            fn = self._lib.mfsr_run if sync else self._lib.mfsr_run_async
+            check(fn(self._h, C.c_void_p(ptr), ow * 12, 1), "mfsr_run")
+            self._keep_out = out
             return out
         if out is None:
             out = torch.empty((oh, ow, 3), dtype=torch.float32, device=f"cuda:{self.device}")
@@ -154,7 +157,8 @@ class BurstSuperResolution:
         return out
 
     def synchronize(self):
-        check(self._lib.mfsr_synchronize(self._h), "mfsr_synchronize")
+        if self._h:
+            check(self._lib.mfsr_synchronize(self._h), "mfsr_synchronize")
 
     # -- introspection used by tests / bench
     def stage_ms(self) -> dict:

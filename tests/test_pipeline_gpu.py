@@ -118,3 +118,30 @@ def test_api_errors(cuda_device):
     with pytest.raises(MfsrError):
         BurstSuperResolution(p2, 0, 128, 128, 2).workspace_bytes
     sr.close()
+
+
+def test_pipeline_async_two_handles(cuda_device):
+    """mfsr_run_async on two alternating handles (the bench's e2e pattern) returns the same images as the blocking call."""
+    p = default_params()
+    p.levels = 2
+    bursts = [synth_burst(3, 128, 192, seed=40 + i)[0] for i in range(4)]
+    n, h, w = bursts[0].shape
+    ref = []
+    sr = BurstSuperResolution(p, 0, w, h, n)
+    for b in bursts:
+        sr.set_input(u16(b).copy())
+        ref.append(sr.next_frame(host=True).numpy().copy())
+    hs = [sr, BurstSuperResolution(p, 0, w, h, n)]
+    pinned_in = [torch.from_numpy(u16(b).copy().view(np.int16)).pin_memory() for b in bursts]
+    outs = [torch.empty_like(torch.from_numpy(ref[0])).pin_memory() for _ in bursts]
+    for i, b in enumerate(bursts):
+        hd = hs[i % 2]
+        hd.synchronize()
+        hd.set_input(pinned_in[i].numpy().view(np.uint16))
+        hd.next_frame(out=outs[i], host=True, sync=False)
+    for hd in hs:
+        hd.synchronize()
+    for i in range(4):
+        assert np.array_equal(outs[i].numpy(), ref[i]), i
+    for hd in hs:
+        hd.close()
