@@ -11,14 +11,19 @@ namespace mfsr {
 
 struct Flow2 { float x, y; };
 
-__device__ __forceinline__ Flow2 flow_fetch(const float2* __restrict__ flow, int64_t pitch, int fw, int fh, float px_half, float py_half, int w, int h)
+// Flow "texture" fetch at half-resolution pixel centre (px, py): normalised coordinate (px + .5) / w on a texture of
+// width 2w lands at texel coordinate 2 px + 1 (+- one ulp of the division, far from any rounding boundary), i.e. exactly
+// between texels 2px and 2px+1 with the 1.8 fixed-point fraction 128/256: the bilinear fetch is tex_mix(..., .5, .5) of the
+// four (clamped) texels.  Bit-identical to the generic tex_coord/tex_axis path it replaces, without its two IEEE divisions.
+__device__ __forceinline__ Flow2 flow_fetch_half(const float2* __restrict__ flow, int64_t pitch, int fw, int fh, int px, int py)
 {
-    const TexAxis ax = tex_axis(tex_coord(px_half, w, fw), fw), ay = tex_axis(tex_coord(py_half, h, fh), fh);
-    const float2 t00 = row_ptr(flow, pitch, ay.i0)[ax.i0], t10 = row_ptr(flow, pitch, ay.i0)[ax.i1];
-    const float2 t01 = row_ptr(flow, pitch, ay.i1)[ax.i0], t11 = row_ptr(flow, pitch, ay.i1)[ax.i1];
+    const int x0 = min(2 * px, fw - 1), x1 = min(2 * px + 1, fw - 1), y0 = min(2 * py, fh - 1), y1 = min(2 * py + 1, fh - 1);
+    const float2* r0 = row_ptr(flow, pitch, y0);
+    const float2* r1 = row_ptr(flow, pitch, y1);
+    const float2 t00 = __ldg(r0 + x0), t10 = __ldg(r0 + x1), t01 = __ldg(r1 + x0), t11 = __ldg(r1 + x1);
     Flow2 r;
-    r.x = tex_mix(t00.x, t10.x, t01.x, t11.x, ax.a, ay.a);
-    r.y = tex_mix(t00.y, t10.y, t01.y, t11.y, ax.a, ay.a);
+    r.x = tex_mix(t00.x, t10.x, t01.x, t11.x, 0.5f, 0.5f);
+    r.y = tex_mix(t00.y, t10.y, t01.y, t11.y, 0.5f, 0.5f);
     return r;
 }
 
@@ -33,23 +38,35 @@ robustness_kernel(const float* __restrict__ ref3, const float* __restrict__ mov3
         row_ptr(mask, mask_pitch, py)[px] = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
     }
-    const Flow2 sf = flow_fetch(flow, flow_pitch, fw, fh, (float)px + 0.5f, (float)py + 0.5f, w, h);
-    const Flow2 sl = flow_fetch(flow, flow_pitch, fw, fh, (float)px + 2 + 0.5f, (float)py + 2 + 0.5f, w, h);
+    const Flow2 sf = flow_fetch_half(flow, flow_pitch, fw, fh, px, py);
+    const Flow2 sl = flow_fetch_half(flow, flow_pitch, fw, fh, px + 2, py + 2);
     float maxx = fmaxf(sl.x, sf.x), maxy = fmaxf(sl.y, sf.y), minx = fminf(sl.x, sf.x), miny = fminf(sl.y, sf.y);
     const int shx = (int)roundf(__fmul_rn(sf.x, 0.5f)), shy = (int)roundf(__fmul_rn(sf.y, 0.5f));
     float pix[9][3], meanRef[3] = {0.f, 0.f, 0.f}, meanMov[3] = {0.f, 0.f, 0.f};
+    // reference 3x3 patch: rows py-1..py+1, 9 contiguous floats each
 #pragma unroll
-    for (int y = -1; y <= 1; y++)
+    for (int y = -1; y <= 1; y++) {
+        const float* p = row_ptr(ref3, rgb_pitch, py + y) + 3 * (px - 1);
+#pragma unroll
+        for (int x = 0; x < 3; x++) {
+            const int i = (y + 1) * 3 + x;
+            pix[i][0] = __ldg(p + 3 * x); pix[i][1] = __ldg(p + 3 * x + 1); pix[i][2] = __ldg(p + 3 * x + 2);
+        }
+    }
+    // moved 3x3 patch at the rounded half-resolution shift, clamp addressing (:93-101); same summation order as the reference
+    const int mx = px + shx, my = py + shy;
+    const bool xin = mx >= 1 && mx <= w - 2;
+#pragma unroll
+    for (int y = -1; y <= 1; y++) {
+        const float* q = row_ptr(mov3, rgb_pitch, min(max(my + y, 0), h - 1));
 #pragma unroll
         for (int x = -1; x <= 1; x++) {
-            const float* p = row_ptr(ref3, rgb_pitch, py + y) + 3 * (px + x);
             const int i = (y + 1) * 3 + (x + 1);
-            pix[i][0] = p[0]; pix[i][1] = p[1]; pix[i][2] = p[2];
-            meanRef[0] += p[0]; meanRef[1] += p[1]; meanRef[2] += p[2];
-            const int ppy = min(max(py + shy + y, 0), h - 1), ppx = min(max(px + shx + x, 0), w - 1);
-            const float* q = row_ptr(mov3, rgb_pitch, ppy) + 3 * ppx;
-            meanMov[0] += q[0]; meanMov[1] += q[1]; meanMov[2] += q[2];
+            meanRef[0] += pix[i][0]; meanRef[1] += pix[i][1]; meanRef[2] += pix[i][2];
+            const float* qq = q + 3 * (xin ? mx + x : min(max(mx + x, 0), w - 1));
+            meanMov[0] += __ldg(qq); meanMov[1] += __ldg(qq + 1); meanMov[2] += __ldg(qq + 2);
         }
+    }
 #pragma unroll
     for (int c = 0; c < 3; c++) { meanRef[c] /= 9.0f; meanMov[c] /= 9.0f; }
     float meandist = fabsf(meanRef[0] - meanMov[0]) + fabsf(meanRef[1] - meanMov[1]) + fabsf(meanRef[2] - meanMov[2]);
