@@ -99,16 +99,24 @@ lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const int ox = x0 - HW - 2, oy = y0 - HW - 2;             // global coordinate of s_src[0][0]
 
-    // 1. source + warped moved image (WarpingKernel, opticalFlow.cu:28) on the haloed region, clamp addressing
+    // 1. source + warped moved image (WarpingKernel, opticalFlow.cu:28) on the haloed region, clamp addressing.
+    // tex_coord's (p / n) * n uses a hoisted correctly rounded reciprocal + one FMA correction step (Markstein): the same
+    // correctly rounded quotient as __fdiv_rn without re-deriving the reciprocal and the FCHK slow-path test per element.
+    const float fw = (float)w, fh = (float)h, rw = 1.0f / fw, rh = 1.0f / fh;
+    const int pe = (int)(img_pitch >> 2), pf = (int)(flow_pitch >> 3);          // pitches in elements (checked by the launcher)
     for (int i = tid; i < WW * WH; i += NT) {
         const int ly = i / WW, lx = i - ly * WW;
         const int gx = clampi(ox + lx, 0, w - 1), gy = clampi(oy + ly, 0, h - 1);
-        s_src[ly][lx] = __ldg(row_ptr(ref, img_pitch, gy) + gx);
-        const float2 f = __ldg(row_ptr(flow_in, flow_pitch, gy) + gx);
-        const TexAxis ax = tex_axis(tex_coord((float)gx + 0.5f + f.x, w, w), w);
-        const TexAxis ay = tex_axis(tex_coord((float)gy + 0.5f + f.y, h, h), h);
-        const float* r0 = row_ptr(mov, img_pitch, ay.i0);
-        const float* r1 = row_ptr(mov, img_pitch, ay.i1);
+        s_src[ly][lx] = __ldg(ref + (size_t)(gy * pe + gx));
+        const float2 f = __ldg(flow_in + (size_t)(gy * pf + gx));
+        const float px = (float)gx + 0.5f + f.x, py = (float)gy + 0.5f + f.y;
+        float qx = px * rw, qy = py * rh;
+        qx = __fmaf_rn(__fmaf_rn(-fw, qx, px), rw, qx);
+        qy = __fmaf_rn(__fmaf_rn(-fh, qy, py), rh, qy);
+        const TexAxis ax = tex_axis(__fmul_rn(qx, fw), w);
+        const TexAxis ay = tex_axis(__fmul_rn(qy, fh), h);
+        const float* r0 = mov + (size_t)(ay.i0 * pe);
+        const float* r1 = mov + (size_t)(ay.i1 * pe);
         s_wrp[ly][lx] = tex_mix(__ldg(r0 + ax.i0), __ldg(r0 + ax.i1), __ldg(r1 + ax.i0), __ldg(r1 + ax.i1), ax.a, ay.a);
     }
     __syncthreads();
@@ -215,6 +223,8 @@ extern "C" int mfsr_stage_lk_iteration(const float* ref, const float* mov, int64
 {
     if (!ref || !mov || !flow_in || !flow_out || flow_in == flow_out || width < 1 || height < 1) return MFSR_E_INVALID;
     if (half_window < 1 || half_window > LHW_MAX) return MFSR_E_INVALID;
+    // 32-bit element indexing inside the kernel
+    if ((img_pitch & 3) || (flow_pitch & 7) || (int64_t)(img_pitch >> 2) * height >= (1ll << 31) || (int64_t)(flow_pitch >> 3) * height >= (1ll << 31)) return MFSR_E_INVALID;
     dim3 b(LTW, 8), g(cdiv(width, LTW), cdiv(height, LTH));
     cudaStream_t st = (cudaStream_t)stream;
     switch (half_window) {

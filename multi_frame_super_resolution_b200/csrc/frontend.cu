@@ -56,7 +56,14 @@ struct DemosaicTile {
 
 __device__ __forceinline__ float rawc(float v, int c, const F3& black, const F3& scale) { return (v - black.v[c]) * scale.v[c]; }
 
-template <int TW, int TH, int HR>
+// PN ("pre-normalised"): the raw plane holds (v - black[c]) * scale[c] with c = the CFA colour of the sample's own
+// position, computed once per sample instead of once per use (a sample is used ~8 times by the two demosaic steps).
+// Identical values whenever every colour the reference passes to its RAW macro equals the colour at that position,
+// i.e. for the four Bayer patterns and for an all-green (monochrome) CFA; the host selects PN only then.
+template <bool PN>
+__device__ __forceinline__ float rawv(float v, int c, const F3& black, const F3& scale) { return PN ? v : rawc(v, c, black, scale); }
+
+template <int TW, int TH, int HR, bool PN>
 __device__ void demosaic_stage(DemosaicTile<TW, TH, HR>& S, const uint16_t* __restrict__ raw, int64_t raw_pitch,
                                int w, int h, int x0, int y0, const Cfa& cfa, const F3& black, const F3& scale)
 {
@@ -64,8 +71,11 @@ __device__ void demosaic_stage(DemosaicTile<TW, TH, HR>& S, const uint16_t* __re
     const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
     for (int i = tid; i < DT::RW * DT::RH; i += nthr) {
         const int ry = i / DT::RW, rx = i - ry * DT::RW;
-        const int gx = clampi(x0 - (HR + 3) + rx, 0, w - 1), gy = clampi(y0 - (HR + 3) + ry, 0, h - 1);
-        S.raw[ry][rx] = (float)row_ptr(raw, raw_pitch, gy)[gx];
+        const int nx = x0 - (HR + 3) + rx, ny = y0 - (HR + 3) + ry;
+        const int gx = clampi(nx, 0, w - 1), gy = clampi(ny, 0, h - 1);
+        const float v = (float)row_ptr(raw, raw_pitch, gy)[gx];
+        // out-of-image samples are only read by pixels the reference never writes (2-px border): their value is irrelevant
+        S.raw[ry][rx] = PN ? rawc(v, cfa.c[(ny & 1) * 2 + (nx & 1)], black, scale) : v;
     }
     __syncthreads();
     // green (deBayerGreenKernel, DeBayerKernels.cu:55-149)
@@ -76,13 +86,13 @@ __device__ void demosaic_stage(DemosaicTile<TW, TH, HR>& S, const uint16_t* __re
         if (gx >= 2 && gx < w - 2 && gy >= 2 && gy < h - 2) {
             const int ry = qy + 2, rx = qx + 2;
             const int col = cfa.c[(gy & 1) * 2 + (gx & 1)];
-            if (col == MFSR_GREEN) g = rawc(S.raw[ry][rx], 1, black, scale);
+            if (col == MFSR_GREEN) g = rawv<PN>(S.raw[ry][rx], 1, black, scale);
             else if (col == MFSR_RED || col == MFSR_BLUE) {
-                const float p = rawc(S.raw[ry][rx], col, black, scale);
-                const float xm2 = rawc(S.raw[ry][rx - 2], col, black, scale), xm1 = rawc(S.raw[ry][rx - 1], 1, black, scale);
-                const float xp1 = rawc(S.raw[ry][rx + 1], 1, black, scale), xp2 = rawc(S.raw[ry][rx + 2], col, black, scale);
-                const float ym2 = rawc(S.raw[ry - 2][rx], col, black, scale), ym1 = rawc(S.raw[ry - 1][rx], 1, black, scale);
-                const float yp1 = rawc(S.raw[ry + 1][rx], 1, black, scale), yp2 = rawc(S.raw[ry + 2][rx], col, black, scale);
+                const float p = rawv<PN>(S.raw[ry][rx], col, black, scale);
+                const float xm2 = rawv<PN>(S.raw[ry][rx - 2], col, black, scale), xm1 = rawv<PN>(S.raw[ry][rx - 1], 1, black, scale);
+                const float xp1 = rawv<PN>(S.raw[ry][rx + 1], 1, black, scale), xp2 = rawv<PN>(S.raw[ry][rx + 2], col, black, scale);
+                const float ym2 = rawv<PN>(S.raw[ry - 2][rx], col, black, scale), ym1 = rawv<PN>(S.raw[ry - 1][rx], 1, black, scale);
+                const float yp1 = rawv<PN>(S.raw[ry + 1][rx], 1, black, scale), yp2 = rawv<PN>(S.raw[ry + 2][rx], col, black, scale);
                 const float gradX = 0.5f * fabsf(xp1 - xm1), gradY = 0.5f * fabsf(yp1 - ym1);
                 const float lapX = 0.25f * fabsf(2.0f * p - xm2 - xp2), lapY = 0.25f * fabsf(2.0f * p - ym2 - yp2);
                 const float ipX = 0.125f * (-xm2 + 4.0f * xm1 + 2.0f * p + 4.0f * xp1 - xp2);
@@ -97,14 +107,14 @@ __device__ void demosaic_stage(DemosaicTile<TW, TH, HR>& S, const uint16_t* __re
 }
 
 // red/blue of one pixel (deBayerRedBlueKernel, :153-231); (lx,ly) relative to the tile origin, in [-HR, T+HR)
-template <int TW, int TH, int HR>
+template <int TW, int TH, int HR, bool PN>
 __device__ __forceinline__ void demosaic_px(const DemosaicTile<TW, TH, HR>& S, int lx, int ly, int gx, int gy, int w, int h,
                                             const Cfa& cfa, const F3& black, const F3& scale, float& r, float& g, float& b)
 {
     r = g = b = 0.f;
     if (gx < 2 || gx >= w - 2 || gy < 2 || gy >= h - 2) return;
     const int qx = lx + HR + 1, qy = ly + HR + 1, rx = lx + HR + 3, ry = ly + HR + 3;
-#define RAWX(dx, dy, c) rawc(S.raw[ry + (dy)][rx + (dx)], c, black, scale)
+#define RAWX(dx, dy, c) rawv<PN>(S.raw[ry + (dy)][rx + (dx)], c, black, scale)
 #define GRNX(dx, dy) S.grn[qy + (dy)][qx + (dx)]
     const int col = cfa.c[(gy & 1) * 2 + (gx & 1)];
     const int row = cfa.c[(gy & 1) * 2 + ((gx + 1) & 1)];
@@ -136,12 +146,12 @@ demosaic_kernel(const uint16_t* __restrict__ raw, int64_t raw_pitch, float* __re
 {
     __shared__ DemosaicTile<DTW, DTH, 0> S;
     const int x0 = blockIdx.x * DTW, y0 = blockIdx.y * DTH;
-    demosaic_stage(S, raw, raw_pitch, w, h, x0, y0, cfa, black, scale);
+    demosaic_stage<DTW, DTH, 0, false>(S, raw, raw_pitch, w, h, x0, y0, cfa, black, scale);
     for (int ly = threadIdx.y; ly < DTH; ly += blockDim.y) {
         const int gx = x0 + threadIdx.x, gy = y0 + ly;
         if (gx >= w || gy >= h) continue;
         float r, g, b;
-        demosaic_px(S, (int)threadIdx.x, ly, gx, gy, w, h, cfa, black, scale, r, g, b);
+        demosaic_px<DTW, DTH, 0, false>(S, (int)threadIdx.x, ly, gx, gy, w, h, cfa, black, scale, r, g, b);
         float* o = row_ptr(rgb, rgb_pitch, gy) + 3 * gx;
         o[0] = r; o[1] = g; o[2] = b;
     }
@@ -151,43 +161,49 @@ demosaic_kernel(const uint16_t* __restrict__ raw, int64_t raw_pitch, float* __re
 constexpr int MAX_TAPS = 9;
 struct Taps { float t[MAX_TAPS]; int n; };
 
-template <int R>
+// 64-wide tiles (TH = 32 rows for R <= 2, 16 for larger blurs: static shared memory <= 48 KB).  The first version used
+// 32x16 tiles and re-normalised every raw sample at every use: 670 instructions per pixel (profiles/r1k).
+template <int R, bool PN>
 __global__ void __launch_bounds__(256)
 tracking_kernel(const uint16_t* __restrict__ raw, int64_t raw_pitch, float* __restrict__ gray, int64_t gray_pitch,
                 uint8_t* __restrict__ gray_q, int64_t gq_pitch, int w, int h, Cfa cfa, F3 black, F3 scale, Taps taps, float qmax)
 {
-    __shared__ DemosaicTile<DTW, DTH, R> S;
-    __shared__ float lum[DTH + 2 * R][DTW + 2 * R];
-    __shared__ float hb[DTH + 2 * R][DTW];
-    const int x0 = blockIdx.x * DTW, y0 = blockIdx.y * DTH;
+    constexpr int TW = 64, TH = (R <= 2) ? 32 : 16;
+    constexpr int LW = TW + 2 * R, LH = TH + 2 * R;
+    __shared__ DemosaicTile<TW, TH, R> S;
+    __shared__ float lum[LH][LW];
+    __shared__ float hb[LH][TW];
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
-    demosaic_stage(S, raw, raw_pitch, w, h, x0, y0, cfa, black, scale);
-    constexpr int LW = DTW + 2 * R, LH = DTH + 2 * R;
+    demosaic_stage<TW, TH, R, PN>(S, raw, raw_pitch, w, h, x0, y0, cfa, black, scale);
     for (int i = tid; i < LW * LH; i += nthr) {
         const int ly = i / LW - R, lx = i % LW - R;
         float r, g, b;
-        demosaic_px(S, lx, ly, x0 + lx, y0 + ly, w, h, cfa, black, scale, r, g, b);
+        demosaic_px<TW, TH, R, PN>(S, lx, ly, x0 + lx, y0 + ly, w, h, cfa, black, scale, r, g, b);
         // out-of-image pixels are never read (clamped indices below)
         lum[ly + R][lx + R] = 0.25f * r + 0.5f * g + 0.25f * b;
     }
     __syncthreads();
     // horizontal pass, clamp border: index = clamp(x+k-c, 0, w-1)
-    for (int i = tid; i < DTW * LH; i += nthr) {
-        const int ry = i / DTW, lx = i - ry * DTW;
+    for (int i = tid; i < TW * LH; i += nthr) {
+        const int ry = i / TW, lx = i - ry * TW;
         const int gx = x0 + lx;
         float acc = 0.f;
-        for (int k = 0; k < taps.n; k++) {
+#pragma unroll
+        for (int k = 0; k < 2 * R + 1; k++) {
             const int sx = clampi(gx + k - R, 0, w - 1) - x0 + R;
             acc += taps.t[k] * lum[ry][clampi(sx, 0, LW - 1)];
         }
         hb[ry][lx] = acc;
     }
     __syncthreads();
-    for (int ly = threadIdx.y; ly < DTH; ly += blockDim.y) {
-        const int lx = threadIdx.x, gx = x0 + lx, gy = y0 + ly;
+    for (int i = tid; i < TW * TH; i += nthr) {
+        const int ly = i / TW, lx = i - ly * TW;
+        const int gx = x0 + lx, gy = y0 + ly;
         if (gx >= w || gy >= h) continue;
         float acc = 0.f;
-        for (int k = 0; k < taps.n; k++) {
+#pragma unroll
+        for (int k = 0; k < 2 * R + 1; k++) {
             const int sy = clampi(gy + k - R, 0, h - 1) - y0 + R;
             acc += taps.t[k] * hb[clampi(sy, 0, LH - 1)][lx];
         }
@@ -280,16 +296,24 @@ extern "C" int mfsr_stage_tracking_image(const uint16_t* raw, int64_t raw_pitch,
     t.n = gauss_taps(sigma, t.t);
     if (t.n < 0) return MFSR_E_INVALID;
     const float qmax = (float)((1 << track_bits) - 1);
-    dim3 b(DTW, 8), g(cdiv(width, DTW), cdiv(height, DTH));
     const Cfa c = mk_cfa(cfa); const F3 bl = mk_f3(black), sc = mk_f3(scale);
     cudaStream_t st = (cudaStream_t)stream;
-    switch (t.n / 2) {
-        case 1: tracking_kernel<1><<<g, b, 0, st>>>(raw, raw_pitch, gray, gray_pitch, gray_q, gray_q_pitch, width, height, c, bl, sc, t, qmax); break;
-        case 2: tracking_kernel<2><<<g, b, 0, st>>>(raw, raw_pitch, gray, gray_pitch, gray_q, gray_q_pitch, width, height, c, bl, sc, t, qmax); break;
-        case 3: tracking_kernel<3><<<g, b, 0, st>>>(raw, raw_pitch, gray, gray_pitch, gray_q, gray_q_pitch, width, height, c, bl, sc, t, qmax); break;
-        case 4: tracking_kernel<4><<<g, b, 0, st>>>(raw, raw_pitch, gray, gray_pitch, gray_q, gray_q_pitch, width, height, c, bl, sc, t, qmax); break;
-        default: return MFSR_E_INVALID;
+    // pre-normalised raw plane: Bayer patterns (greens on one diagonal, red/blue on the other) or monochrome
+    const bool mono = cfa[0] == 1 && cfa[1] == 1 && cfa[2] == 1 && cfa[3] == 1;
+    const bool bayer = (cfa[1] == 1 && cfa[2] == 1 && cfa[0] != 1 && cfa[3] != 1 && cfa[0] != cfa[3]) ||
+                       (cfa[0] == 1 && cfa[3] == 1 && cfa[1] != 1 && cfa[2] != 1 && cfa[1] != cfa[2]);
+    const bool pn = mono || bayer;
+    const int R = t.n / 2;
+    if (R < 1 || R > 4) return MFSR_E_INVALID;
+    dim3 b(64, 4), g(cdiv(width, 64), cdiv(height, R <= 2 ? 32 : 16));
+#define MFSR_TRK(RR, PP) tracking_kernel<RR, PP><<<g, b, 0, st>>>(raw, raw_pitch, gray, gray_pitch, gray_q, gray_q_pitch, width, height, c, bl, sc, t, qmax)
+    switch (R * 2 + (pn ? 1 : 0)) {
+        case 2: MFSR_TRK(1, false); break;  case 3: MFSR_TRK(1, true); break;
+        case 4: MFSR_TRK(2, false); break;  case 5: MFSR_TRK(2, true); break;
+        case 6: MFSR_TRK(3, false); break;  case 7: MFSR_TRK(3, true); break;
+        case 8: MFSR_TRK(4, false); break;  default: MFSR_TRK(4, true); break;
     }
+#undef MFSR_TRK
     MFSR_LAUNCH_CHECK();
     return MFSR_OK;
 }
