@@ -216,6 +216,184 @@ tracking_kernel(const uint16_t* __restrict__ raw, int64_t raw_pitch, float* __re
     }
 }
 
+// ---------------------------------------------------------------- tracking image, quad form
+// Bayer / monochrome fast path.  Tiles are 64x32 with an even origin, so the CFA colour of every sample of a 2x2 quad
+// is a COMPILE-TIME function of the pattern PAT (c00 | c10 << 2 | c01 << 4 | c11 << 6, row-major like c_cfaPattern) and
+// of the region's origin parity: a thread processes whole quads with straight-line code — no per-sample colour lookups
+// in the kernel-parameter bank (78 LDC + 105 ISETP per pixel in the element-wise version, profiles/r1m).
+// Arithmetic (operation order, -fmad=false) is identical to deBayerGreenKernel / deBayerRedBlueKernel
+// (DeBayerKernels.cu:55-231) on pre-normalised samples (see rawv above), followed by the restated luma + Gaussian.
+template <int PAT> __device__ __forceinline__ constexpr int pat_col(int x, int y) { return (PAT >> (2 * ((y & 1) * 2 + (x & 1)))) & 3; }
+
+template <int COL, int ROW, int RP, int GP>
+__device__ __forceinline__ float px_luma(const float* __restrict__ rw, const float* __restrict__ gr)
+{
+    // rw / gr point at the pixel inside the normalised raw plane (pitch RP) and the green plane (pitch GP)
+    const float g = gr[0];
+    float r, b;
+#define RW_(dx, dy) rw[(dy) * RP + (dx)]
+#define GR_(dx, dy) gr[(dy) * GP + (dx)]
+    if (COL == MFSR_GREEN) {
+        const float hz = g + 0.5f * ((RW_(-1, 0) - GR_(-1, 0)) + (RW_(1, 0) - GR_(1, 0)));
+        const float vt = g + 0.5f * ((RW_(0, -1) - GR_(0, -1)) + (RW_(0, 1) - GR_(0, 1)));
+        if (ROW == MFSR_RED) { r = hz; b = vt; } else { b = hz; r = vt; }
+    } else {
+        const float dg = g + 0.25f * ((RW_(-1, -1) - GR_(-1, -1)) + (RW_(1, -1) - GR_(1, -1)) + (RW_(1, 1) - GR_(1, 1)) + (RW_(-1, 1) - GR_(-1, 1)));
+        if (COL == MFSR_RED) { r = RW_(0, 0); b = dg; } else { b = RW_(0, 0); r = dg; }
+    }
+#undef RW_
+#undef GR_
+    return 0.25f * r + 0.5f * g + 0.25f * b;
+}
+
+template <int COL, int RP>
+__device__ __forceinline__ float px_green(const float* __restrict__ rw)
+{
+    if (COL == MFSR_GREEN) return rw[0];
+    const float p = rw[0];
+    const float xm2 = rw[-2], xm1 = rw[-1], xp1 = rw[1], xp2 = rw[2];
+    const float ym2 = rw[-2 * RP], ym1 = rw[-RP], yp1 = rw[RP], yp2 = rw[2 * RP];
+    const float gradX = 0.5f * fabsf(xp1 - xm1), gradY = 0.5f * fabsf(yp1 - ym1);
+    const float lapX = 0.25f * fabsf(2.0f * p - xm2 - xp2), lapY = 0.25f * fabsf(2.0f * p - ym2 - yp2);
+    const float ipX = 0.125f * (-xm2 + 4.0f * xm1 + 2.0f * p + 4.0f * xp1 - xp2);
+    const float ipY = 0.125f * (-ym2 + 4.0f * ym1 + 2.0f * p + 4.0f * yp1 - yp2);
+    const float wgt = (gradY + lapY) / (gradX + gradY + lapX + lapY + 0.000000001f);
+    return wgt * ipX + (1.0f - wgt) * ipY;
+}
+
+template <int R, int PAT>
+__global__ void __launch_bounds__(256)
+tracking_quad_kernel(const uint16_t* __restrict__ raw, int64_t raw_pitch, float* __restrict__ gray, int64_t gray_pitch,
+                     uint8_t* __restrict__ gray_q, int64_t gq_pitch, int w, int h, F3 black, F3 scale, Taps taps, float qmax)
+{
+    constexpr int TW = 64, TH = 32;
+    constexpr int RW = TW + 2 * (R + 3), RH = TH + 2 * (R + 3);      // normalised raw plane, origin (x0 - R - 3, y0 - R - 3)
+    constexpr int GW = TW + 2 * (R + 1), GH = TH + 2 * (R + 1);      // green plane,          origin (x0 - R - 1, y0 - R - 1)
+    constexpr int LW = TW + 2 * R, LH = TH + 2 * R;                  // luma,                 origin (x0 - R, y0 - R)
+    constexpr int LWP = LW + (LW & 1), LHP = LH + (LH & 1);          // luma computed on whole quads
+    constexpr int PR = (R + 3) & 1, PG = (R + 1) & 1, PL = R & 1;    // origin parities (tile origins are even)
+    __shared__ __align__(8) float s_raw[RH][RW];
+    __shared__ float s_grn[GH][GW];
+    __shared__ float s_lum[LHP][LWP];
+    __shared__ float s_hb[LH][TW];
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    constexpr int NT = 256;
+
+    // ---- normalised raw plane, one 2x2 quad per iteration
+    {
+        const int ox = x0 - (R + 3), oy = y0 - (R + 3);
+        const bool inside = ox >= 0 && oy >= 0 && ox + RW <= w && oy + RH <= h && !(raw_pitch & 3) && !((uintptr_t)raw & 3) && !(ox & 1);
+        for (int q = tid; q < (RW / 2) * (RH / 2); q += NT) {
+            const int qy = q / (RW / 2), qx = q - qy * (RW / 2);
+            const int rx = 2 * qx, ry = 2 * qy;
+            float v[2][2];
+            if (inside) {
+#pragma unroll
+                for (int dy = 0; dy < 2; dy++) {
+                    const unsigned u = *(const unsigned*)(row_ptr(raw, raw_pitch, oy + ry + dy) + ox + rx);
+                    v[dy][0] = (float)(u & 0xffffu); v[dy][1] = (float)(u >> 16);
+                }
+            } else {
+#pragma unroll
+                for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+                    for (int dx = 0; dx < 2; dx++)
+                        v[dy][dx] = (float)row_ptr(raw, raw_pitch, clampi(oy + ry + dy, 0, h - 1))[clampi(ox + rx + dx, 0, w - 1)];
+            }
+#pragma unroll
+            for (int dy = 0; dy < 2; dy++) {
+                const int c0 = pat_col<PAT>(PR, dy + PR), c1 = pat_col<PAT>(1 + PR, dy + PR);
+                *(float2*)&s_raw[ry + dy][rx] = make_float2((v[dy][0] - black.v[c0]) * scale.v[c0], (v[dy][1] - black.v[c1]) * scale.v[c1]);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- green plane (deBayerGreenKernel): zero outside [2, dim-2)
+    {
+        const int ox = x0 - (R + 1), oy = y0 - (R + 1);
+        const bool interior = ox >= 2 && oy >= 2 && ox + GW <= w - 2 && oy + GH <= h - 2;
+        for (int q = tid; q < (GW / 2) * (GH / 2); q += NT) {
+            const int qy = q / (GW / 2), qx = q - qy * (GW / 2);
+            const int gx0 = 2 * qx, gy0 = 2 * qy;
+            const float* rw = &s_raw[gy0 + 2][gx0 + 2];
+            float g[2][2];
+            g[0][0] = px_green<pat_col<PAT>(PG, PG), RW>(rw);
+            g[0][1] = px_green<pat_col<PAT>(1 + PG, PG), RW>(rw + 1);
+            g[1][0] = px_green<pat_col<PAT>(PG, 1 + PG), RW>(rw + RW);
+            g[1][1] = px_green<pat_col<PAT>(1 + PG, 1 + PG), RW>(rw + RW + 1);
+            if (!interior) {
+#pragma unroll
+                for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+                    for (int dx = 0; dx < 2; dx++) {
+                        const int ax = ox + gx0 + dx, ay = oy + gy0 + dy;
+                        if (ax < 2 || ax >= w - 2 || ay < 2 || ay >= h - 2) g[dy][dx] = 0.f;
+                    }
+            }
+            s_grn[gy0][gx0] = g[0][0]; s_grn[gy0][gx0 + 1] = g[0][1]; s_grn[gy0 + 1][gx0] = g[1][0]; s_grn[gy0 + 1][gx0 + 1] = g[1][1];
+        }
+    }
+    __syncthreads();
+    // ---- red / blue (deBayerRedBlueKernel) + luma 0.25 R + 0.5 G + 0.25 B on the blur's support
+    {
+        const int ox = x0 - R, oy = y0 - R;
+        const bool interior = ox >= 2 && oy >= 2 && ox + LWP <= w - 2 && oy + LHP <= h - 2;
+        for (int q = tid; q < (LWP / 2) * (LHP / 2); q += NT) {
+            const int qy = q / (LWP / 2), qx = q - qy * (LWP / 2);
+            const int lx0 = 2 * qx, ly0 = 2 * qy;
+            const float* rw = &s_raw[ly0 + 3][lx0 + 3];
+            const float* gr = &s_grn[ly0 + 1][lx0 + 1];
+            float l[2][2];
+            l[0][0] = px_luma<pat_col<PAT>(PL, PL), pat_col<PAT>(1 + PL, PL), RW, GW>(rw, gr);
+            l[0][1] = px_luma<pat_col<PAT>(1 + PL, PL), pat_col<PAT>(PL, PL), RW, GW>(rw + 1, gr + 1);
+            l[1][0] = px_luma<pat_col<PAT>(PL, 1 + PL), pat_col<PAT>(1 + PL, 1 + PL), RW, GW>(rw + RW, gr + GW);
+            l[1][1] = px_luma<pat_col<PAT>(1 + PL, 1 + PL), pat_col<PAT>(PL, 1 + PL), RW, GW>(rw + RW + 1, gr + GW + 1);
+            if (!interior) {
+#pragma unroll
+                for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+                    for (int dx = 0; dx < 2; dx++) {
+                        const int ax = ox + lx0 + dx, ay = oy + ly0 + dy;
+                        if (ax < 2 || ax >= w - 2 || ay < 2 || ay >= h - 2) l[dy][dx] = 0.f;     // r = g = b = 0 (unwritten border)
+                    }
+            }
+            s_lum[ly0][lx0] = l[0][0]; s_lum[ly0][lx0 + 1] = l[0][1]; s_lum[ly0 + 1][lx0] = l[1][0]; s_lum[ly0 + 1][lx0 + 1] = l[1][1];
+        }
+    }
+    __syncthreads();
+    // ---- separable Gaussian, clamp border (index = clamp(x + k - c, 0, w - 1)), quantisation
+    const bool edge = x0 - R < 0 || y0 - R < 0 || x0 + TW + R > w || y0 + TH + R > h;
+    for (int i = tid; i < TW * LH; i += NT) {
+        const int ry = i / TW, lx = i - ry * TW;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 2 * R + 1; k++) {
+            const int sx = edge ? clampi(clampi(x0 + lx + k - R, 0, w - 1) - x0 + R, 0, LW - 1) : lx + k;
+            acc += taps.t[k] * s_lum[ry][sx];
+        }
+        s_hb[ry][lx] = acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < TW * TH; i += NT) {
+        const int ly = i / TW, lx = i - ly * TW;
+        const int gx = x0 + lx, gy = y0 + ly;
+        if (gx >= w || gy >= h) continue;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 2 * R + 1; k++) {
+            const int sy = edge ? clampi(clampi(gy + k - R, 0, h - 1) - y0 + R, 0, LH - 1) : ly + k;
+            acc += taps.t[k] * s_hb[sy][lx];
+        }
+        if (gray) row_ptr(gray, gray_pitch, gy)[gx] = acc;
+        if (gray_q) {
+            float q = floorf(acc * qmax + 0.5f);
+            q = fminf(fmaxf(q, 0.0f), qmax);
+            row_ptr(gray_q, gq_pitch, gy)[gx] = (uint8_t)q;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- pyramid
 __global__ void __launch_bounds__(256)
 pyramid_down_kernel(const uint8_t* __restrict__ in, int64_t in_pitch, uint8_t* __restrict__ out, int64_t out_pitch, int ow, int oh)
@@ -305,6 +483,19 @@ extern "C" int mfsr_stage_tracking_image(const uint16_t* raw, int64_t raw_pitch,
     const bool pn = mono || bayer;
     const int R = t.n / 2;
     if (R < 1 || R > 4) return MFSR_E_INVALID;
+    if (pn && R <= 2) {
+        const int pat = cfa[0] | (cfa[1] << 2) | (cfa[2] << 4) | (cfa[3] << 6);
+        dim3 bq(64, 4), gq(cdiv(width, 64), cdiv(height, 32));
+#define MFSR_TQ(RR, PP) tracking_quad_kernel<RR, PP><<<gq, bq, 0, st>>>(raw, raw_pitch, gray, gray_pitch, gray_q, gray_q_pitch, width, height, bl, sc, t, qmax)
+#define MFSR_TQP(PP) if (pat == (PP)) { if (R == 1) MFSR_TQ(1, PP); else MFSR_TQ(2, PP); MFSR_LAUNCH_CHECK(); return MFSR_OK; }
+        MFSR_TQP(0 | (1 << 2) | (1 << 4) | (2 << 6))      // RGGB
+        MFSR_TQP(2 | (1 << 2) | (1 << 4) | (0 << 6))      // BGGR
+        MFSR_TQP(1 | (0 << 2) | (2 << 4) | (1 << 6))      // GRBG
+        MFSR_TQP(1 | (2 << 2) | (0 << 4) | (1 << 6))      // GBRG
+        MFSR_TQP(1 | (1 << 2) | (1 << 4) | (1 << 6))      // monochrome
+#undef MFSR_TQP
+#undef MFSR_TQ
+    }
     dim3 b(64, 4), g(cdiv(width, 64), cdiv(height, R <= 2 ? 32 : 16));
 #define MFSR_TRK(RR, PP) tracking_kernel<RR, PP><<<g, b, 0, st>>>(raw, raw_pitch, gray, gray_pitch, gray_q, gray_q_pitch, width, height, c, bl, sc, t, qmax)
     switch (R * 2 + (pn ? 1 : 0)) {
