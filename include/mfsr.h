@@ -290,7 +290,8 @@ int64_t mfsr_workspace_bytes(mfsr_handle h);
 
 /* frames[i]: pointer to frame i (u16, row pitch `pitch` bytes).  on_host != 0:
  * pointers are HOST memory (pinned or pageable) and are copied H2D on the
- * handle's stream; otherwise they are device pointers and are used in place. */
+ * handle's stream; otherwise they are device pointers: an evenly spaced stack with a 16-byte aligned base and
+ * pitch is used IN PLACE (keep it alive and unchanged until the run has finished), anything else is copied. */
 int mfsr_set_frames(mfsr_handle h, const void* const* frames, int n, int width, int height,
                     int64_t pitch, int format, int ref_idx, int on_host);
 /* Runs the whole chain on the handle's stream.  `out`: float3 image

@@ -387,31 +387,37 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
     {
         const int mw = g.raw_w / 2, mh = g.raw_h / 2;
         const int mx0 = (X0abs >> 2) - 1, my0 = (Y0abs >> 2) - 1;
-        // fixed mask pixel per thread, frames in batches of 4 loads
-        for (int ii = tid; ii < C::PLANE; ii += C::NT) {
-            const int r = ii / MWS, c = ii - r * MWS;
-            float2* ms = (float2*)(smem + C::SHIFT_BYTES + C::RAW_BYTES) + ii;
-            const char* mp = (const char*)A.mask + A.mask_pitch * clampi(my0 + r, 0, mh - 1) + 16 * clampi(mx0 + c, 0, mw - 1);
-            for (int f0 = 0; f0 < N; f0 += 4) {
-                float4 m4[4];
+        // (frame, mask pixel) items flattened over the block (balanced: the barrier below waits for the slowest warp),
+        // 4 loads in flight per thread
+        const int nmask = N * C::PLANE;
+        for (int i0 = tid; i0 < nmask; i0 += 4 * C::NT) {
+            float4 m4[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (f0 + k < N) m4[k] = __ldg((const float4*)(mp + A.mask_fs * (f0 + k)));
+            for (int k = 0; k < 4; k++) {
+                const int i = i0 + k * C::NT;
+                if (i < nmask) {
+                    const int f = i / C::PLANE, ii = i - f * C::PLANE;
+                    const int r = ii / MWS, c = ii - r * MWS;
+                    m4[k] = __ldg((const float4*)((const char*)A.mask + A.mask_fs * f + A.mask_pitch * clampi(my0 + r, 0, mh - 1) + 16 * clampi(mx0 + c, 0, mw - 1)));
+                }
+            }
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (f0 + k < N) {
-                        const float4 m = m4[k];
-                        const float ch[3] = {isfinite(m.x) ? m.x : 0.f, isfinite(m.y) ? m.y : 0.f, isfinite(m.z) ? m.z : 0.f};   // :438-439
-                        float q4[4];
+            for (int k = 0; k < 4; k++) {
+                const int i = i0 + k * C::NT;
+                if (i < nmask) {
+                    const int f = i / C::PLANE, ii = i - f * C::PLANE;
+                    const float4 m = m4[k];
+                    const float ch[3] = {isfinite(m.x) ? m.x : 0.f, isfinite(m.y) ? m.y : 0.f, isfinite(m.z) ? m.z : 0.f};   // :438-439
+                    float q4[4];
 #pragma unroll
-                        for (int q = 0; q < 4; q++) { const int col = A.cfa.c[q]; q4[q] = col == 0 ? ch[0] : (col == 1 ? ch[1] : ch[2]); }
-                        // plane = xswap * 2 + absolute y phase; element = (x class 0, x class 1)
-                        float2* m2 = ms + (size_t)(f0 + k) * (C::FRAME_BYTES / 8);
-                        m2[0 * C::PLANE] = make_float2(q4[0], q4[1]);
-                        m2[1 * C::PLANE] = make_float2(q4[2], q4[3]);
-                        m2[2 * C::PLANE] = make_float2(q4[1], q4[0]);
-                        m2[3 * C::PLANE] = make_float2(q4[3], q4[2]);
-                    }
+                    for (int q = 0; q < 4; q++) { const int col = A.cfa.c[q]; q4[q] = col == 0 ? ch[0] : (col == 1 ? ch[1] : ch[2]); }
+                    // plane = xswap * 2 + absolute y phase; element = (x class 0, x class 1)
+                    float2* m2 = (float2*)(smem + (size_t)f * C::FRAME_BYTES + C::SHIFT_BYTES + C::RAW_BYTES) + ii;
+                    m2[0 * C::PLANE] = make_float2(q4[0], q4[1]);
+                    m2[1 * C::PLANE] = make_float2(q4[2], q4[3]);
+                    m2[2 * C::PLANE] = make_float2(q4[1], q4[0]);
+                    m2[3 * C::PLANE] = make_float2(q4[3], q4[2]);
+                }
             }
         }
         // kernel parameters (texture clamp addressing applied here)
@@ -436,37 +442,41 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
     // 4-column chunks (r, c4) of the window and walks the frames, 4 loads in flight
     {
         constexpr int CH = C::RHS * (RWS / 4);
-        for (int ii = tid; ii < CH; ii += C::NT) {
-            const int r = ii / (RWS / 4), c4 = ii - r * (RWS / 4);
-            float* rs0 = (float*)(smem + C::SHIFT_BYTES) + r * RWS + 2 * c4;
-            for (int f0 = 0; f0 < N; f0 += 4) {
-                uint2 p4[4]; int ph4[4]; bool in4[4];
+        const int nraw = N * CH;
+        for (int i0 = tid; i0 < nraw; i0 += 4 * C::NT) {
+            uint2 p4[4]; int ph4[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (f0 + k < N) {
-                        const int2 fi = fbase[f0 + k];
-                        const int yy = clampi(fi.y + r, 0, g.raw_h - 1), xx = fi.x + 4 * c4;
-                        const uint16_t* rrow = (const uint16_t*)((const char*)A.raw + A.raw_fs * (f0 + k) + A.raw_pitch * yy);
-                        ph4[k] = (yy & 1) * 2;                               // xx is a multiple of 4
-                        in4[k] = xx >= 0 && xx + 3 < g.raw_w;
-                        if (in4[k]) p4[k] = __ldg((const uint2*)(rrow + xx));
-                        else {
-                            unsigned v[4];
+            for (int k = 0; k < 4; k++) {
+                const int i = i0 + k * C::NT;
+                if (i < nraw) {
+                    const int f = i / CH, ii = i - f * CH;
+                    const int r = ii / (RWS / 4), c4 = ii - r * (RWS / 4);
+                    const int2 fi = fbase[f];
+                    const int yy = clampi(fi.y + r, 0, g.raw_h - 1), xx = fi.x + 4 * c4;
+                    const uint16_t* rrow = (const uint16_t*)((const char*)A.raw + A.raw_fs * f + A.raw_pitch * yy);
+                    ph4[k] = (yy & 1) * 2;                               // xx is a multiple of 4
+                    if (xx >= 0 && xx + 3 < g.raw_w) p4[k] = __ldg((const uint2*)(rrow + xx));
+                    else {
+                        unsigned v[4];
 #pragma unroll
-                            for (int q = 0; q < 4; q++) v[q] = __ldg(rrow + clampi(xx + q, 0, g.raw_w - 1));
-                            p4[k] = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
-                        }
+                        for (int q = 0; q < 4; q++) v[q] = __ldg(rrow + clampi(xx + q, 0, g.raw_w - 1));
+                        p4[k] = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
                     }
+                }
+            }
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (f0 + k < N) {
-                        const uint2 p = p4[k];
-                        const int ph = ph4[k];
-                        const float be = F.black_ph[ph], bo = F.black_ph[ph + 1], ie = F.inv_ph[ph], io = F.inv_ph[ph + 1];
-                        float* rs = rs0 + (size_t)(f0 + k) * (C::FRAME_BYTES / 4);
-                        *(float2*)rs = make_float2(((float)(p.x & 0xffffu) - be) * ie, ((float)(p.y & 0xffffu) - be) * ie);
-                        *(float2*)(rs + RHALF) = make_float2(((float)(p.x >> 16) - bo) * io, ((float)(p.y >> 16) - bo) * io);
-                    }
+            for (int k = 0; k < 4; k++) {
+                const int i = i0 + k * C::NT;
+                if (i < nraw) {
+                    const int f = i / CH, ii = i - f * CH;
+                    const int r = ii / (RWS / 4), c4 = ii - r * (RWS / 4);
+                    const uint2 p = p4[k];
+                    const int ph = ph4[k];
+                    const float be = F.black_ph[ph], bo = F.black_ph[ph + 1], ie = F.inv_ph[ph], io = F.inv_ph[ph + 1];
+                    float* rs = (float*)(smem + (size_t)f * C::FRAME_BYTES + C::SHIFT_BYTES) + r * RWS + 2 * c4;
+                    *(float2*)rs = make_float2(((float)(p.x & 0xffffu) - be) * ie, ((float)(p.y & 0xffffu) - be) * ie);
+                    *(float2*)(rs + RHALF) = make_float2(((float)(p.x >> 16) - bo) * io, ((float)(p.y >> 16) - bo) * io);
+                }
             }
         }
     }

@@ -36,7 +36,8 @@ struct mfsr_context {
     int n, w, h, ref_idx, format; bool have_frames, ran;
     int launches;
     // buffers (all inside ws)
-    uint16_t* raw; int64_t raw_pitch, raw_fs;
+    uint16_t* raw; int64_t raw_pitch, raw_fs;          // workspace copy of the frames
+    const uint16_t* rawp; int64_t rawp_pitch, rawp_fs; // the stack the kernels read: the copy, or the caller's frames in place
     float* rgb_half; int64_t rgbh_pitch, rgbh_fs;
     float* gray; int64_t gray_pitch, gray_fs;
     float* rgb_ref; int64_t rgb_pitch;
@@ -260,10 +261,21 @@ extern "C" int mfsr_set_frames(mfsr_handle h, const void* const* frames, int n, 
             h->pt.from[h->m] = (int8_t)i; h->pt.to[h->m] = (int8_t)j; h->m++;
         }
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_UPLOAD], h->stream));
-    for (int f = 0; f < n; f++) {
+    for (int f = 0; f < n; f++)
         if (!frames[f]) return MFSR_E_INVALID;
-        MFSR_CUDA_TRY(cudaMemcpy2DAsync((char*)h->raw + h->raw_fs * f, h->raw_pitch, frames[f], pitch, (size_t)width * 2, height,
-                                        on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+    // Device frames that form an evenly spaced, vector-load-aligned stack are used IN PLACE (no staging copy);
+    // the caller keeps them alive until the run has finished.  Anything else is copied into the workspace.
+    bool in_place = !on_host && !((uintptr_t)frames[0] & 15) && !(pitch & 15);
+    int64_t stride = n > 1 ? (const char*)frames[1] - (const char*)frames[0] : pitch * height;
+    for (int f = 1; in_place && f < n; f++) in_place = ((const char*)frames[f] - (const char*)frames[0]) == stride * f;
+    if (in_place && n > 1 && (stride < pitch * height || (stride & 15))) in_place = false;
+    if (in_place) {
+        h->rawp = (const uint16_t*)frames[0]; h->rawp_pitch = pitch; h->rawp_fs = stride;
+    } else {
+        for (int f = 0; f < n; f++)
+            MFSR_CUDA_TRY(cudaMemcpy2DAsync((char*)h->raw + h->raw_fs * f, h->raw_pitch, frames[f], pitch, (size_t)width * 2, height,
+                                            on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+        h->rawp = h->raw; h->rawp_pitch = h->raw_pitch; h->rawp_fs = h->raw_fs;
     }
     h->have_frames = true; h->ran = false;
     return MFSR_OK;
@@ -294,16 +306,16 @@ static int run_impl(mfsr_handle h, float* out, int64_t out_pitch, int out_on_hos
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_FRONTEND], st));
     const float maxVal = p.white_level[1] + p.black_level[1];
     for (int f = 0; f < n; f++) {
-        const uint16_t* raw = (const uint16_t*)((const char*)h->raw + h->raw_fs * f);
-        RUN(mfsr_stage_subsample3(raw, h->raw_pitch, (float*)((char*)h->rgb_half + h->rgbh_fs * f), h->rgbh_pitch, maxVal, hw2, hh2, cfa, st));
-        RUN(mfsr_stage_tracking_image(raw, h->raw_pitch, (float*)((char*)h->gray + h->gray_fs * f), h->gray_pitch,
+        const uint16_t* raw = (const uint16_t*)((const char*)h->rawp + h->rawp_fs * f);
+        RUN(mfsr_stage_subsample3(raw, h->rawp_pitch, (float*)((char*)h->rgb_half + h->rgbh_fs * f), h->rgbh_pitch, maxVal, hw2, hh2, cfa, st));
+        RUN(mfsr_stage_tracking_image(raw, h->rawp_pitch, (float*)((char*)h->gray + h->gray_fs * f), h->gray_pitch,
                                       h->lv[0].img + h->lv[0].frame_stride * f, h->lv[0].pitch, w, hh, cfa, p.black_level, scale,
                                       p.track_sigma, p.track_bits, st));
         for (size_t l = 1; l < h->lv.size(); l++)
             RUN(mfsr_stage_pyramid_down(h->lv[l - 1].img + h->lv[l - 1].frame_stride * f, h->lv[l - 1].pitch, h->lv[l - 1].w, h->lv[l - 1].h,
                                         h->lv[l].img + h->lv[l].frame_stride * f, h->lv[l].pitch, st));
     }
-    RUN(mfsr_stage_demosaic((const uint16_t*)((const char*)h->raw + h->raw_fs * h->ref_idx), h->raw_pitch, h->rgb_ref, h->rgb_pitch,
+    RUN(mfsr_stage_demosaic((const uint16_t*)((const char*)h->rawp + h->rawp_fs * h->ref_idx), h->rawp_pitch, h->rgb_ref, h->rgb_pitch,
                             w, hh, cfa, p.black_level, scale, st));
 
     // ---- C. pyramid tile matching, all measured pairs per launch, coarse -> fine
@@ -382,7 +394,7 @@ static int run_impl(mfsr_handle h, float* out, int64_t out_pitch, int out_on_hos
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_MERGE], st));
     float* dst = out_on_host ? h->outbuf : out;
     const int64_t dst_pitch = out_on_host ? h->out_pitch_own : out_pitch;
-    RUN(mfsr_stage_merge(h->raw, h->raw_pitch, h->raw_fs, (const float*)h->mask, h->mask_pitch, h->mask_fs,
+    RUN(mfsr_stage_merge(h->rawp, h->rawp_pitch, h->rawp_fs, (const float*)h->mask, h->mask_pitch, h->mask_fs,
                          (const float*)cur, h->flow_pitch, h->flow_fs, (const float*)h->kern, h->kern_pitch,
                          h->fallback, h->out_pitch_own, dst, dst_pitch, nullptr, nullptr, 0, n, &h->geom, cfa,
                          p.white_level, p.black_level, p.weight_threshold, p.merge_flags & ~MFSR_MERGE_NO_FALLBACK, st));
@@ -450,7 +462,7 @@ extern "C" int mfsr_get_buffer(mfsr_handle h, const char* name, void** dev_ptr, 
     if (!h || !name || !dev_ptr) return MFSR_E_INVALID;
     if (!h->have_frames) return MFSR_E_STATE;
     int64_t pi = 0, fs = 0; void* p = nullptr;
-    if (!strcmp(name, "raw")) { p = h->raw; pi = h->raw_pitch; fs = h->raw_fs; }
+    if (!strcmp(name, "raw")) { p = (void*)h->rawp; pi = h->rawp_pitch; fs = h->rawp_fs; }
     else if (!strcmp(name, "rgb_half")) { p = h->rgb_half; pi = h->rgbh_pitch; fs = h->rgbh_fs; }
     else if (!strcmp(name, "gray")) { p = h->gray; pi = h->gray_pitch; fs = h->gray_fs; }
     else if (!strcmp(name, "gray_q0")) { p = h->lv[0].img; pi = h->lv[0].pitch; fs = h->lv[0].frame_stride; }
