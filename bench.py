@@ -239,7 +239,7 @@ def main():
                 "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": int(n * h * w * 2), "d2h_bytes_per_step": int(ow * oh * 12),
                         "ms_per_step": round(float(t2.item()), 3), "timed": "host wall clock over the steps: mfsr_set_frames(pinned host) + mfsr_run_async(pinned host out) on two alternating handles (transfers of one burst overlap kernels of the other), all synchronised at the end; max over ranks"},
                 "gpu_launches": int(launches),
-                "roofline": {"kernel": "merge (mfsr_stage_merge)", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "roofline": {"kernel": "merge_s2_dyn_kernel (mfsr_stage_merge)", "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                              "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                              "bytes_per_output_px": bpp, "ms_per_launch": round(mm, 4)},
                 "stage_ms": {k: round(v, 3) for k, v in stage_last.items()},

@@ -1,0 +1,127 @@
+#!/usr/bin/env python
+"""`multi_frame_sr`-compatible command line for the B200 burst path.
+
+Mirrors finalProject/Project/multi_frame_sr.cpp:122-209:
+
+    python -m multi_frame_super_resolution_b200.cli optFlowName inputName iterations
+
+* inputName city / car / iso selects `img_%06d.png` (5 frames; the repo ships 000000..000004, the program asks
+  for 000001..000005 — both numberings are tried), `car/%d.jpg` (4), `iso/%06d.png` (4) in the current directory
+  (:151-163); any other value is taken as a printf-style pattern with `--frames N`.
+* optFlowName is accepted for compatibility (farneback / tvl1 / brox / pyrlk select OpenCV flows in the reference,
+  :61-87); this path always uses its own tile aligner + Lucas-Kanade refinement, `iterations` sets the LK sweeps.
+* scale 2, the burst is processed `num_times = 10` times and the last `real_times = 5` repetitions are timed (:146-149);
+  prints "<t> sec" and "<fps> FPS" (:204-206), writes <input>_<flow>_sr_result.png and the Laplacian-sharpened
+  <input>_<flow>_sr2_result.png (:90-119, :207-209), plus one JSON line with MP/s.
+
+8-bit colour frames are mosaiced to RGGB and mapped to the 10-bit range of the default parameters
+(raw = round(v8 * 959 / 255) + 64), exactly like tests/golden/make_bundled_fixture.py.
+All arithmetic runs in libmfsr_b200.so; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import json
+import sys
+import time
+
+import numpy as np
+
+
+def _mosaic_rggb(bgr: np.ndarray) -> np.ndarray:
+    rgb = bgr[..., ::-1].astype(np.float64)
+    h, w = rgb.shape[:2]
+    h, w = h & ~1, w & ~1
+    raw = np.empty((h, w), np.float64)
+    raw[0::2, 0::2] = rgb[0:h:2, 0:w:2, 0]
+    raw[0::2, 1::2] = rgb[0:h:2, 1:w:2, 1]
+    raw[1::2, 0::2] = rgb[1:h:2, 0:w:2, 1]
+    raw[1::2, 1::2] = rgb[1:h:2, 1:w:2, 2]
+    return (np.round(raw * 959.0 / 255.0) + 64).astype(np.uint16)
+
+
+def _sharpen(img8: np.ndarray) -> np.ndarray:
+    """sharpenImg2 (multi_frame_sr.cpp:90-119): img - 0.5 * Laplacian, saturated."""
+    import cv2
+    lap = cv2.Laplacian(img8.astype(np.float32), cv2.CV_32F, ksize=3)
+    return np.clip(img8.astype(np.float32) - 0.5 * lap, 0, 255).astype(np.uint8)
+
+
+def main(argv=None) -> int:
+    argv = list(sys.argv[1:] if argv is None else argv)
+    n_override = None
+    if "--frames" in argv:
+        i = argv.index("--frames")
+        n_override = int(argv[i + 1])
+        del argv[i:i + 2]
+    if len(argv) == 0:
+        flow, name, iterations = "farneback", "city", 10
+    elif len(argv) == 3:
+        flow, name, iterations = argv[0], argv[1], max(1, int(argv[2]))
+    else:
+        print("./multi_frame_sr optFlowName inputName iterations")
+        print("\toptFlowName: farneback, tvl1, brox, pyrlk")
+        print("\tinputName: city, car, iso")
+        print("\titerations: integer, 1, 10, etc.")
+        return -1
+    patterns = {"city": (5, "img_%06d.png"), "car": (4, "car/%d.jpg"), "iso": (4, "iso/%06d.png")}
+    if name in patterns:
+        n, fmt = patterns[name]
+    elif n_override:
+        n, fmt = n_override, name
+    else:
+        print("wrong input")
+        return -1
+    import cv2
+    import torch
+    from .pipeline import BurstSuperResolution, default_params
+
+    frames = []
+    for base in (1, 0):                       # the program asks for 1-based names, the repo ships 0-based city frames
+        frames = []
+        for i in range(n):
+            path = fmt % (i + base)
+            img = cv2.imread(path, cv2.IMREAD_COLOR)
+            if img is None:
+                frames = []
+                break
+            print(f"{path}, [{img.shape[1]} x {img.shape[0]}]")
+            frames.append(_mosaic_rggb(img))
+        if frames:
+            break
+    if not frames:
+        print(f"cannot read {fmt % 1}")
+        return -1
+    raw = np.stack(frames)
+    n, h, w = raw.shape
+    p = default_params()
+    p.scale = 2
+    p.lk_iterations = iterations
+    p.merge_flags = 1                         # GammasRGB: the result is written as an 8-bit image
+    while p.levels > 1 and min(h, w) >> (p.levels - 1) < 2 * p.max_shift + p.tile_size:
+        p.levels -= 1
+    sr = BurstSuperResolution(p, device=0, max_width=w, max_height=h, max_frames=n)
+    dev = torch.from_numpy(raw.view(np.int16)).cuda()
+    num_times, real_times = 10, 5
+    out = None
+    for t in range(num_times):
+        if t == num_times - real_times:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        sr.set_input(dev)
+        out = sr.next_frame()
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    print(f"{sec:.6g} sec")
+    print(f"{real_times * n / sec:.6g} FPS")
+    img = out.cpu().numpy()
+    img8 = np.clip(np.nan_to_num(img) * 255.0 + 0.5, 0, 255).astype(np.uint8)[..., ::-1]
+    cv2.imwrite(f"{name if name in patterns else 'burst'}_{flow}_sr_result.png", img8)
+    cv2.imwrite(f"{name if name in patterns else 'burst'}_{flow}_sr2_result.png", _sharpen(img8))
+    print(json.dumps({"output_megapixels_per_second": round(real_times * img.shape[0] * img.shape[1] / 1e6 / sec, 2),
+                      "frames": n, "raw": [w, h], "scale": 2, "lk_iterations": iterations}))
+    sr.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -130,3 +130,32 @@ def test_merge_full_size_properties(cuda_device):
     fbs = fb[2000:2256, 3000:3512].contiguous()
     outs = stages.merge(raw, mask, flow, kern, fbs, sub, WHITE, BLACK, 0.1)
     assert torch.equal(outs[1:-1, 1:-1], out[2001:2255, 3001:3511])
+
+
+@pytest.mark.parametrize("n", [12, 20, 33])
+def test_merge_many_frames_tile_variants(cuda_device, n):
+    """More frames than the 16-row tile variant can keep resident in shared memory: the 8- and 4-row variants of
+    merge_s2_dyn (and, beyond them, the generic kernel) must give the same image."""
+    h, w = 64, 96
+    raw, mask, flow, kern, g = _inputs(n, h, w, 100 + n, cuda_device)
+    flow[1, 10:30, 20:60, 0] += 9.0            # alignment outliers: window not staged -> global raw fetch
+    flow[2, 40:50, :, 1] -= 40.0
+    geom = MergeGeom.full_frame(w, h, 2)
+    fb = torch.rand((geom.out_h, geom.out_w, 3), generator=g)
+    out, s, wt, exp, es, ew = _run_both(raw, mask, flow, kern, fb, geom, cuda_device)
+    assert max_abs(out, exp) <= TOL_MAXABS and psnr(out, exp) >= TOL_PSNR
+
+
+def test_merge_window_offsets_and_odd_geometry(cuda_device):
+    """Output windows whose origin is not a multiple of 4 (tile grid starts left of / above the window) and whose size is
+    not a multiple of the tile; shifts near the +-127 limit of the char2 encoding and beyond it (sentinel path)."""
+    n, h, w = 3, 96, 128
+    raw, mask, flow, kern, g = _inputs(n, h, w, 321, cuda_device)
+    flow[1, 20:30, 30:50, 0] = 63.4            # 2 * 63.4 -> 127
+    flow[1, 30:40, 30:50, 0] = 64.0            # 128 -> outsized: recomputed per pixel
+    flow[2, 50:60, 10:40, 1] = -70.0
+    for (ow, oh, ox, oy) in ((101, 67, 3, 5), (64, 40, 130, 61), (200, 150, 1, 2)):
+        geom = MergeGeom(w, h, 2, ow, oh, ox, oy, 0, w - 1, 0, h - 1)
+        fb = torch.rand((oh, ow, 3), generator=g)
+        out, s, wt, exp, es, ew = _run_both(raw, mask, flow, kern, fb, geom, cuda_device)
+        assert max_abs(out, exp) <= TOL_MAXABS, (ow, oh, ox, oy)
