@@ -500,7 +500,7 @@ int launch_th(const FastArgs& F, cudaStream_t st)
     const size_t smem = (size_t)C::FRAME_BYTES * F.a.n_frames + C::KERN_BYTES;
     static bool configured = false;
     if (!configured) {
-        MFSR_CUDA_TRY(cudaFuncSetAttribute(merge_s2_dyn_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MFSR_CUDA_TRY(cudaFuncSetAttribute(merge_s2_dyn_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         configured = true;
     }
     dim3 grid(cdiv(g.out_w + F.x_off, TW), cdiv(g.out_h + F.y_off, TH));
@@ -527,7 +527,7 @@ int launch_merge_s2(const MergeArgs& A, cudaStream_t st)
     F.x_off = g.org_x & 3; F.y_off = g.org_y & 3;
     static const char* thenv = getenv("MFSR_MERGE_TH");
     const int want = thenv ? atoi(thenv) : 0;
-    const size_t n = (size_t)A.n_frames, budget1 = 200 * 1024;
+    const size_t n = (size_t)A.n_frames, budget1 = 226 * 1024 - 2048;     // 227 KB per block on sm_100, static tables included
     if (want == 24 && n * DCfg<24>::FRAME_BYTES + DCfg<24>::KERN_BYTES <= budget1) return launch_th<24>(F, st);
     if (want == 8 && n * DCfg<8>::FRAME_BYTES + DCfg<8>::KERN_BYTES <= budget1) return launch_th<8>(F, st);
     if (n * DCfg<16>::FRAME_BYTES + DCfg<16>::KERN_BYTES <= budget1) return launch_th<16>(F, st);
