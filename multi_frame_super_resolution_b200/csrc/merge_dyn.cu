@@ -300,7 +300,7 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
     using C = DCfg<TH>;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int2 fbase[MAXF];           // origin (rx0, ry0) of the staged raw window per frame
-    __shared__ int s_sum[MAXF][3];         // sum sx, sum sy, count of the tile's (non-outsized) shifts
+    __shared__ int s_part[MAXF * (TH / 2)][3];   // per (frame, row pair) item: sum sx, sum sy, count of sampled (non-outsized) shifts
     const MergeArgs& A = F.a;
     const mfsr_merge_geom& g = A.g;
     const int N = A.n_frames;
@@ -308,8 +308,6 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
     const int x0 = (int)blockIdx.x * TW - F.x_off, y0 = (int)blockIdx.y * TH - F.y_off;   // window coords of the tile origin
     const int X0abs = x0 + g.org_x, Y0abs = y0 + g.org_y;                                // multiples of 4
 
-    for (int f = tid; f < N; f += C::NT) { s_sum[f][0] = 0; s_sum[f][1] = 0; s_sum[f][2] = 0; }
-    __syncthreads();
 
     // ---------------- phase 0: integer HR shifts of every tile pixel and frame -> char2 in shared memory.
     // Work item = (frame, row pair): 8 pixels per lane from a 3 x 4 flow window.  Two items are in flight per warp
@@ -366,7 +364,7 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
             *(uint2*)(sh + ((2 * rp + 1) * TW + 4 * lane) * 2) = make_uint2(packed[1][0], packed[1][1]);
             sum_x = __reduce_add_sync(0xffffffffu, sum_x); sum_y = __reduce_add_sync(0xffffffffu, sum_y);
             cnt = __reduce_add_sync(0xffffffffu, cnt);
-            if (lane == 0) { atomicAdd(&s_sum[f][0], sum_x); atomicAdd(&s_sum[f][1], sum_y); atomicAdd(&s_sum[f][2], cnt); }
+            if (lane == 0) { s_part[item][0] = sum_x; s_part[item][1] = sum_y; s_part[item][2] = cnt; }
         };
         float2 FA[3][4], FB[3][4];
         int item = warp;
@@ -429,14 +427,17 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
         }
     }
     __syncthreads();
-    for (int f = tid; f < N; f += C::NT) {
-        // staged raw window: the tile's own footprint displaced by the MEAN shift, spare rows/columns split evenly
-        const int cnt = max(s_sum[f][2], 1);
-        const int mx = (int)floorf((float)s_sum[f][0] / (float)cnt + 0.5f), my = (int)floorf((float)s_sum[f][1] / (float)cnt + 0.5f);
+    // staged raw window: the tile's own footprint displaced by the MEAN shift, spare rows/columns split evenly.  Every warp
+    // derives the (identical) origins itself — a benign same-value race instead of a second block barrier.
+    for (int f = lane; f < N; f += 32) {
+        int sx = 0, sy = 0, cnt = 0;
+        for (int k = 0; k < TH / 2; k++) { sx += s_part[f * (TH / 2) + k][0]; sy += s_part[f * (TH / 2) + k][1]; cnt += s_part[f * (TH / 2) + k][2]; }
+        cnt = max(cnt, 1);
+        const int mx = (int)floorf((float)sx / (float)cnt + 0.5f), my = (int)floorf((float)sy / (float)cnt + 0.5f);
         fbase[f] = make_int2((((X0abs + mx - 2) >> 1) - (RWS - (TW / 2 + 3)) / 2) & ~3,
                              ((Y0abs + my - 2) >> 1) - (C::RHS - (TH / 2 + 3)) / 2);
     }
-    __syncthreads();
+    __syncwarp();
 
     // ---------------- phase 1b: normalised raw windows (de-interleaved by column parity); a thread owns fixed
     // 4-column chunks (r, c4) of the window and walks the frames, 4 loads in flight
@@ -498,11 +499,16 @@ int launch_th(const FastArgs& F, cudaStream_t st)
     using C = DCfg<TH>;
     const mfsr_merge_geom& g = F.a.g;
     const size_t smem = (size_t)C::FRAME_BYTES * F.a.n_frames + C::KERN_BYTES;
-    static bool configured = false;
-    if (!configured) {
-        MFSR_CUDA_TRY(cudaFuncSetAttribute(merge_s2_dyn_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        configured = true;
+    // opt-in shared memory: 227 KB per block on sm_100 minus this instantiation's static tables
+    static size_t max_dyn = 0;
+    if (!max_dyn) {
+        cudaFuncAttributes at;
+        MFSR_CUDA_TRY(cudaFuncGetAttributes(&at, merge_s2_dyn_kernel<TH>));
+        const size_t lim = (size_t)227 * 1024 - at.sharedSizeBytes;
+        MFSR_CUDA_TRY(cudaFuncSetAttribute(merge_s2_dyn_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+        max_dyn = lim;
     }
+    if (smem > max_dyn) return MFSR_E_INVALID;
     dim3 grid(cdiv(g.out_w + F.x_off, TW), cdiv(g.out_h + F.y_off, TH));
     merge_s2_dyn_kernel<TH><<<grid, C::NT, smem, st>>>(F);
     MFSR_LAUNCH_CHECK();
@@ -527,13 +533,14 @@ int launch_merge_s2(const MergeArgs& A, cudaStream_t st)
     F.x_off = g.org_x & 3; F.y_off = g.org_y & 3;
     static const char* thenv = getenv("MFSR_MERGE_TH");
     const int want = thenv ? atoi(thenv) : 0;
-    const size_t n = (size_t)A.n_frames, budget1 = 226 * 1024 - 2048;     // 227 KB per block on sm_100, static tables included
-    if (want == 24 && n * DCfg<24>::FRAME_BYTES + DCfg<24>::KERN_BYTES <= budget1) return launch_th<24>(F, st);
-    if (want == 8 && n * DCfg<8>::FRAME_BYTES + DCfg<8>::KERN_BYTES <= budget1) return launch_th<8>(F, st);
-    if (n * DCfg<16>::FRAME_BYTES + DCfg<16>::KERN_BYTES <= budget1) return launch_th<16>(F, st);
-    if (n * DCfg<8>::FRAME_BYTES + DCfg<8>::KERN_BYTES <= budget1) return launch_th<8>(F, st);
-    if (n * DCfg<4>::FRAME_BYTES + DCfg<4>::KERN_BYTES <= budget1) return launch_th<4>(F, st);
-    return MFSR_E_INVALID;
+    const size_t n = (size_t)A.n_frames, budget1 = 227 * 1024 - 6144;     // dynamic part; launch_th re-checks against the exact limit
+    int rc = MFSR_E_INVALID;
+    if (want == 24 && n * DCfg<24>::FRAME_BYTES + DCfg<24>::KERN_BYTES <= budget1) rc = launch_th<24>(F, st);
+    if (rc == MFSR_E_INVALID && want == 8 && n * DCfg<8>::FRAME_BYTES + DCfg<8>::KERN_BYTES <= budget1) rc = launch_th<8>(F, st);
+    if (rc == MFSR_E_INVALID && n * DCfg<16>::FRAME_BYTES + DCfg<16>::KERN_BYTES <= budget1) rc = launch_th<16>(F, st);
+    if (rc == MFSR_E_INVALID && n * DCfg<8>::FRAME_BYTES + DCfg<8>::KERN_BYTES <= budget1) rc = launch_th<8>(F, st);
+    if (rc == MFSR_E_INVALID && n * DCfg<4>::FRAME_BYTES + DCfg<4>::KERN_BYTES <= budget1) rc = launch_th<4>(F, st);
+    return rc;
 }
 
 }  // namespace mfsr
