@@ -111,7 +111,13 @@ typedef struct mfsr_params {
     /* merge */
     float weight_threshold;   /* ApplyWeighting threshold (kernel.cu:433)                    */
     int   merge_flags;        /* MFSR_MERGE_*                                                */
-    int   reserved[8];
+    /* Row-band mode (one very large burst split over GPUs): the frames given to mfsr_set_frames are
+     * rows [band_row0, band_row0 + height) of a burst that is band_global_h rows tall; only output rows
+     * s*[band_keep_row0, band_keep_row0 + band_keep_rows) (LOCAL raw rows) are produced.  band_row0 must be a
+     * multiple of tile_size << (levels - 1) so that the tile and pyramid grids coincide with the full-frame ones;
+     * base_rotation must be 0.  All zero = not a band. */
+    int   band_global_h, band_row0, band_keep_row0, band_keep_rows;
+    int   reserved[4];
 } mfsr_params;
 
 int         mfsr_abi_version(void);

@@ -37,7 +37,8 @@ class Params(C.Structure):
         ("Dth", c_f), ("Dtr", c_f), ("kDetail", c_f), ("kDenoise", c_f), ("kStretch", c_f), ("kShrink", c_f),
         ("tensor_box_radius", c_i),
         ("alpha", c_f), ("beta", c_f), ("thresholdM", c_f), ("mask_erode_radius", c_i),
-        ("weight_threshold", c_f), ("merge_flags", c_i), ("reserved", c_i * 8),
+        ("weight_threshold", c_f), ("merge_flags", c_i),
+        ("band_global_h", c_i), ("band_row0", c_i), ("band_keep_row0", c_i), ("band_keep_rows", c_i), ("reserved", c_i * 4),
     ]
 
 

@@ -7,23 +7,27 @@
 // column sums) instead of two full (2h+1)^2 passes per pixel.
 // HBM traffic per sweep: ref gray 4 B + moved gray (gather, ~4 B) + flow 8 B in, 8 B out.
 #include "common.cuh"
+#include "internal.h"
 
 namespace mfsr {
 
-// CreateFlowFieldFromTiles (opticalFlow.cu:48-93)
+// CreateFlowFieldFromTiles (opticalFlow.cu:48-93).  Band form: see internal.h (gh == h, gy0 == 0, gty == tilesY, trow0 == 0
+// for a whole frame).
 __global__ void __launch_bounds__(256)
 flow_from_tiles_kernel(const float2* __restrict__ tiles, int64_t tile_pitch, int tilesX, int tilesY,
-                       float2* __restrict__ flow, int64_t flow_pitch, int w, int h, float bsx, float bsy, float cr, float sr)
+                       float2* __restrict__ flow, int64_t flow_pitch, int w, int h, float bsx, float bsy, float cr, float sr,
+                       int gh, int gy0, int gty, int trow0)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
     float sx = cr * -bsx - sr * -bsy;
     float sy = sr * -bsx + cr * -bsy;
-    const float pcx = (float)(x - w / 2), pcy = (float)(y - h / 2);
+    const float pcx = (float)(x - w / 2), pcy = (float)(y + gy0 - gh / 2);
     sx += cr * pcx - sr * pcy - pcx;
     sy += sr * pcx + cr * pcy - pcy;
     const TexAxis ax = tex_axis(tex_coord((float)x + 0.5f, w, tilesX), tilesX);
-    const TexAxis ay = tex_axis(tex_coord((float)y + 0.5f, h, tilesY), tilesY);
+    TexAxis ay = tex_axis(tex_coord((float)(y + gy0) + 0.5f, gh, gty), gty);
+    ay.i0 = clampi(ay.i0 - trow0, 0, tilesY - 1); ay.i1 = clampi(ay.i1 - trow0, 0, tilesY - 1);
     const float2 t00 = row_ptr(tiles, tile_pitch, ay.i0)[ax.i0], t10 = row_ptr(tiles, tile_pitch, ay.i0)[ax.i1];
     const float2 t01 = row_ptr(tiles, tile_pitch, ay.i1)[ax.i0], t11 = row_ptr(tiles, tile_pitch, ay.i1)[ax.i1];
     sx += tex_mix(t00.x, t10.x, t01.x, t11.x, ax.a, ay.a);
@@ -83,8 +87,10 @@ template <int HW>
 __global__ void __launch_bounds__(256, 3)
 lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov, int64_t img_pitch,
                     const float2* __restrict__ flow_in, float2* __restrict__ flow_out, int64_t flow_pitch,
-                    int w, int h, float minDet)
+                    int w, int h, float minDet, int gh, int gy0)
 {
+    // gh / gy0: height of the full frame and global row of local row 0 (row-band mode; gh == h, gy0 == 0 otherwise): the warp's
+    // texture coordinates are normalised by the FULL frame so that a band reproduces the full-frame arithmetic bit for bit
     constexpr int RW = LTW + 2 * HW, RH = LTH + 2 * HW;       // derivative region
     constexpr int WW = RW + 4, WH = RH + 4;                   // source / warped region
     constexpr int NT = 256;
@@ -102,19 +108,20 @@ lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov
     // 1. source + warped moved image (WarpingKernel, opticalFlow.cu:28) on the haloed region, clamp addressing.
     // tex_coord's (p / n) * n uses a hoisted correctly rounded reciprocal + one FMA correction step (Markstein): the same
     // correctly rounded quotient as __fdiv_rn without re-deriving the reciprocal and the FCHK slow-path test per element.
-    const float fw = (float)w, fh = (float)h, rw = 1.0f / fw, rh = 1.0f / fh;
+    const float fw = (float)w, fh = (float)gh, rw = 1.0f / fw, rh = 1.0f / fh;
     const int pe = (int)(img_pitch >> 2), pf = (int)(flow_pitch >> 3);          // pitches in elements (checked by the launcher)
     for (int i = tid; i < WW * WH; i += NT) {
         const int ly = i / WW, lx = i - ly * WW;
         const int gx = clampi(ox + lx, 0, w - 1), gy = clampi(oy + ly, 0, h - 1);
         s_src[ly][lx] = __ldg(ref + (size_t)(gy * pe + gx));
         const float2 f = __ldg(flow_in + (size_t)(gy * pf + gx));
-        const float px = (float)gx + 0.5f + f.x, py = (float)gy + 0.5f + f.y;
+        const float px = (float)gx + 0.5f + f.x, py = (float)(gy + gy0) + 0.5f + f.y;
         float qx = px * rw, qy = py * rh;
         qx = __fmaf_rn(__fmaf_rn(-fw, qx, px), rw, qx);
         qy = __fmaf_rn(__fmaf_rn(-fh, qy, py), rh, qy);
         const TexAxis ax = tex_axis(__fmul_rn(qx, fw), w);
-        const TexAxis ay = tex_axis(__fmul_rn(qy, fh), h);
+        TexAxis ay = tex_axis(__fmul_rn(qy, fh), gh);
+        ay.i0 = clampi(ay.i0 - gy0, 0, h - 1); ay.i1 = clampi(ay.i1 - gy0, 0, h - 1);
         const float* r0 = mov + (size_t)(ay.i0 * pe);
         const float* r1 = mov + (size_t)(ay.i1 * pe);
         s_wrp[ly][lx] = tex_mix(__ldg(r0 + ax.i0), __ldg(r0 + ax.i1), __ldg(r1 + ax.i0), __ldg(r1 + ax.i1), ax.a, ay.a);
@@ -205,15 +212,41 @@ lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov
 
 using namespace mfsr;
 
+int mfsr::launch_flow_from_tiles(const float2* tiles, int64_t tile_pitch, int tilesX, int tilesY, float2* flow, int64_t flow_pitch, int w, int h,
+                                 float bsx, float bsy, float rot, int gh, int gy0, int gty, int tile_row0, cudaStream_t st)
+{
+    if (!tiles || !flow || tilesX < 1 || tilesY < 1 || w < 1 || h < 1) return MFSR_E_INVALID;
+    if (gh <= 0) { gh = h; gy0 = 0; gty = tilesY; tile_row0 = 0; }
+    dim3 b(32, 8), g(cdiv(w, 32), cdiv(h, 8));
+    flow_from_tiles_kernel<<<g, b, 0, st>>>(tiles, tile_pitch, tilesX, tilesY, flow, flow_pitch, w, h, bsx, bsy, cosf(rot), sinf(rot), gh, gy0, gty, tile_row0);
+    MFSR_LAUNCH_CHECK();
+    return MFSR_OK;
+}
+
 extern "C" int mfsr_stage_flow_from_tiles(const float* tile_shift, int64_t tile_pitch, int tilesX, int tilesY, int tile_size,
                                           float* flow, int64_t flow_pitch, int width, int height,
                                           float base_shift_x, float base_shift_y, float base_rotation, void* stream)
 {
     (void)tile_size;
-    if (!tile_shift || !flow || tilesX < 1 || tilesY < 1 || width < 1 || height < 1) return MFSR_E_INVALID;
-    dim3 b(32, 8), g(cdiv(width, 32), cdiv(height, 8));
-    flow_from_tiles_kernel<<<g, b, 0, (cudaStream_t)stream>>>((const float2*)tile_shift, tile_pitch, tilesX, tilesY, (float2*)flow, flow_pitch,
-                                                             width, height, base_shift_x, base_shift_y, cosf(base_rotation), sinf(base_rotation));
+    return launch_flow_from_tiles((const float2*)tile_shift, tile_pitch, tilesX, tilesY, (float2*)flow, flow_pitch, width, height,
+                                  base_shift_x, base_shift_y, base_rotation, 0, 0, 0, 0, (cudaStream_t)stream);
+}
+
+int mfsr::launch_lk_iteration(const float* ref, const float* mov, int64_t img_pitch, const float2* flow_in, float2* flow_out, int64_t flow_pitch,
+                              int width, int height, int half_window, float min_det, int gh, int gy0, cudaStream_t st)
+{
+    if (!ref || !mov || !flow_in || !flow_out || flow_in == flow_out || width < 1 || height < 1) return MFSR_E_INVALID;
+    if (half_window < 1 || half_window > LHW_MAX) return MFSR_E_INVALID;
+    // 32-bit element indexing inside the kernel
+    if ((img_pitch & 3) || (flow_pitch & 7) || (int64_t)(img_pitch >> 2) * height >= (1ll << 31) || (int64_t)(flow_pitch >> 3) * height >= (1ll << 31)) return MFSR_E_INVALID;
+    if (gh <= 0) { gh = height; gy0 = 0; }
+    dim3 b(LTW, 8), g(cdiv(width, LTW), cdiv(height, LTH));
+    switch (half_window) {
+        case 1: lk_iteration_kernel<1><<<g, b, 0, st>>>(ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0); break;
+        case 2: lk_iteration_kernel<2><<<g, b, 0, st>>>(ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0); break;
+        case 3: lk_iteration_kernel<3><<<g, b, 0, st>>>(ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0); break;
+        default: lk_iteration_kernel<4><<<g, b, 0, st>>>(ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0); break;
+    }
     MFSR_LAUNCH_CHECK();
     return MFSR_OK;
 }
@@ -221,18 +254,6 @@ extern "C" int mfsr_stage_flow_from_tiles(const float* tile_shift, int64_t tile_
 extern "C" int mfsr_stage_lk_iteration(const float* ref, const float* mov, int64_t img_pitch, const float* flow_in, float* flow_out,
                                        int64_t flow_pitch, int width, int height, int half_window, float min_det, void* stream)
 {
-    if (!ref || !mov || !flow_in || !flow_out || flow_in == flow_out || width < 1 || height < 1) return MFSR_E_INVALID;
-    if (half_window < 1 || half_window > LHW_MAX) return MFSR_E_INVALID;
-    // 32-bit element indexing inside the kernel
-    if ((img_pitch & 3) || (flow_pitch & 7) || (int64_t)(img_pitch >> 2) * height >= (1ll << 31) || (int64_t)(flow_pitch >> 3) * height >= (1ll << 31)) return MFSR_E_INVALID;
-    dim3 b(LTW, 8), g(cdiv(width, LTW), cdiv(height, LTH));
-    cudaStream_t st = (cudaStream_t)stream;
-    switch (half_window) {
-        case 1: lk_iteration_kernel<1><<<g, b, 0, st>>>(ref, mov, img_pitch, (const float2*)flow_in, (float2*)flow_out, flow_pitch, width, height, min_det); break;
-        case 2: lk_iteration_kernel<2><<<g, b, 0, st>>>(ref, mov, img_pitch, (const float2*)flow_in, (float2*)flow_out, flow_pitch, width, height, min_det); break;
-        case 3: lk_iteration_kernel<3><<<g, b, 0, st>>>(ref, mov, img_pitch, (const float2*)flow_in, (float2*)flow_out, flow_pitch, width, height, min_det); break;
-        default: lk_iteration_kernel<4><<<g, b, 0, st>>>(ref, mov, img_pitch, (const float2*)flow_in, (float2*)flow_out, flow_pitch, width, height, min_det); break;
-    }
-    MFSR_LAUNCH_CHECK();
-    return MFSR_OK;
+    return launch_lk_iteration(ref, mov, img_pitch, (const float2*)flow_in, (float2*)flow_out, flow_pitch, width, height, half_window, min_det,
+                               0, 0, (cudaStream_t)stream);
 }

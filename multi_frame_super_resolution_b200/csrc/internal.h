@@ -34,4 +34,14 @@ int launch_consolidate(const float2* measured, int64_t tile_stride, int64_t pair
                        int imageCount, int nTiles, int referenceImage, float2* one_to_one, float2* frame_shift,
                        int* status, cudaStream_t st);
 
+// CreateFlowFieldFromTiles for a row band: pixel rows and tile rows are mapped through the FULL frame's normalised texture
+// coordinates (global height gh, global tile rows gty; local row 0 is global row gy0, local tile row 0 is global tile row
+// gy0 / T) so that a band reproduces the full-frame flow.  gh == 0: plain local mapping.
+int launch_flow_from_tiles(const float2* tiles, int64_t tile_pitch, int tilesX, int tilesY, float2* flow, int64_t flow_pitch, int w, int h,
+                           float bsx, float bsy, float rot, int gh, int gy0, int gty, int tile_row0, cudaStream_t st);
+
+// one Lucas-Kanade sweep; gh / gy0 as above (0: whole frame)
+int launch_lk_iteration(const float* ref, const float* mov, int64_t img_pitch, const float2* flow_in, float2* flow_out, int64_t flow_pitch,
+                        int width, int height, int half_window, float min_det, int gh, int gy0, cudaStream_t st);
+
 }  // namespace mfsr

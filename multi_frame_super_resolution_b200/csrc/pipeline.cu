@@ -55,7 +55,12 @@ struct mfsr_context {
 static void make_geom(const mfsr_params& p, int w, int h, mfsr_merge_geom* g)
 {
     g->raw_w = w; g->raw_h = h; g->scale = p.scale;
-    if (p.full_frame) {
+    if (p.band_global_h > 0) {
+        // row band: only the kept rows are merged; taps of kept rows stay inside the band (halo), so the clamp range is the band
+        const int keep0 = p.band_keep_row0, keepn = p.band_keep_rows > 0 ? p.band_keep_rows : h - p.band_keep_row0;
+        g->out_w = w * p.scale; g->out_h = keepn * p.scale; g->org_x = 0; g->org_y = keep0 * p.scale;
+        g->clamp_x0 = 0; g->clamp_x1 = w - 1; g->clamp_y0 = 0; g->clamp_y1 = h - 1;
+    } else if (p.full_frame) {
         g->out_w = w * p.scale; g->out_h = h * p.scale; g->org_x = 0; g->org_y = 0;
         g->clamp_x0 = 0; g->clamp_x1 = w - 1; g->clamp_y0 = 0; g->clamp_y1 = h - 1;
     } else {
@@ -124,6 +129,11 @@ static int validate_params(const mfsr_params* p)
     if (p->lk_iterations < 0 || p->lk_half_window < 1 || p->lk_half_window > 4) return MFSR_E_INVALID;
     if (p->tensor_box_radius < 0 || p->tensor_box_radius > 3 || p->mask_erode_radius < 0 || p->mask_erode_radius > 8) return MFSR_E_INVALID;
     for (int i = 0; i < 4; i++) if (p->cfa[i] < 0 || p->cfa[i] > 2) return MFSR_E_INVALID;
+    if (p->band_global_h < 0 || p->band_row0 < 0 || p->band_keep_row0 < 0 || p->band_keep_rows < 0) return MFSR_E_INVALID;
+    if (p->band_global_h > 0) {
+        const int grid = p->tile_size << (p->levels - 1);
+        if (!p->full_frame || p->base_rotation != 0.0f || (p->band_row0 % grid) || p->band_row0 >= p->band_global_h) return MFSR_E_INVALID;
+    }
     return MFSR_OK;
 }
 
@@ -152,8 +162,8 @@ static size_t carve(mfsr_context* c, char* base, int n, int w, int h)
     c->kern = (float4*)take((size_t)c->kern_pitch * h);
     mfsr_merge_geom g; make_geom(p, w, h, &g);
     c->out_pitch_own = (int64_t)g.out_w * 12;
-    c->fallback = (float*)take((size_t)c->out_pitch_own * g.out_h);
-    c->outbuf = (float*)take((size_t)c->out_pitch_own * g.out_h);
+    c->fallback = (float*)take((size_t)c->out_pitch_own * (g.out_h + 2));      // + 2: a band's merge window grows by one
+    c->outbuf = (float*)take((size_t)c->out_pitch_own * (g.out_h + 2));        //      row at each interior seam
     // measured pairs
     int m = 0;
     for (int i = 0; i < n; i++) for (int j = i + 1; j < n && j - i <= p.pair_span; j++) m++;
@@ -358,18 +368,19 @@ static int run_impl(mfsr_handle h, float* out, int64_t out_pitch, int out_on_hos
     // ---- E. dense flow + Lucas-Kanade refinement
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_FLOW], st));
     float2* cur = h->flowA; float2* nxt = h->flowB;
+    const int gh = p.band_global_h, gty = gh > 0 ? (gh - 2 * p.max_shift) / p.tile_size : 0;
     for (int f = 0; f < n; f++)
-        RUN(mfsr_stage_flow_from_tiles((const float*)(h->frame_shift + (size_t)f * nt), (int64_t)tx * 8, tx, ty, p.tile_size,
-                                       (float*)((char*)cur + h->flow_fs * f), h->flow_pitch, w, hh, p.base_shift[0], p.base_shift[1], p.base_rotation, st));
+        RUN(launch_flow_from_tiles(h->frame_shift + (size_t)f * nt, (int64_t)tx * 8, tx, ty, (float2*)((char*)cur + h->flow_fs * f), h->flow_pitch,
+                                   w, hh, p.base_shift[0], p.base_shift[1], p.base_rotation, gh, p.band_row0, gty, p.band_row0 / p.tile_size, st));
     for (int it = 0; it < p.lk_iterations; it++) {
         for (int f = 0; f < n; f++) {
             if (f == h->ref_idx) {   // reference against itself: Iz == 0 -> UV == 0, flow unchanged
                 MFSR_CUDA_TRY(cudaMemcpyAsync((char*)nxt + h->flow_fs * f, (char*)cur + h->flow_fs * f, h->flow_fs, cudaMemcpyDeviceToDevice, st));
                 continue;
             }
-            RUN(mfsr_stage_lk_iteration((const float*)((const char*)h->gray + h->gray_fs * h->ref_idx), (const float*)((const char*)h->gray + h->gray_fs * f),
-                                        h->gray_pitch, (const float*)((const char*)cur + h->flow_fs * f), (float*)((char*)nxt + h->flow_fs * f),
-                                        h->flow_pitch, w, hh, p.lk_half_window, p.lk_min_det, st));
+            RUN(launch_lk_iteration((const float*)((const char*)h->gray + h->gray_fs * h->ref_idx), (const float*)((const char*)h->gray + h->gray_fs * f),
+                                    h->gray_pitch, (const float2*)((const char*)cur + h->flow_fs * f), (float2*)((char*)nxt + h->flow_fs * f),
+                                    h->flow_pitch, w, hh, p.lk_half_window, p.lk_min_det, gh, p.band_row0, st));
         }
         float2* t = cur; cur = nxt; nxt = t;
     }
@@ -389,18 +400,31 @@ static int run_impl(mfsr_handle h, float* out, int64_t out_pitch, int out_on_hos
     }
     // ---- fallback image (ApplyWeighting's inOutImg): demosaiced reference on the output grid
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_FALLBACK], st));
-    RUN(mfsr_stage_fallback_upsample(h->rgb_ref, h->rgb_pitch, w, hh, h->fallback, h->out_pitch_own, &h->geom, st));
+    // Row-band mode: the reference leaves the 1-pixel border of the merge WINDOW untouched (DeBayerKernels.cu:391).  At an
+    // interior seam that border must not exist, so the window is grown by one output row there, merged into the handle's
+    // own buffer, and the kept rows are copied out.
+    mfsr_merge_geom mg = h->geom;
+    int ext_top = 0, ext_bot = 0;
+    if (p.band_global_h > 0) {
+        const int keepn = h->geom.out_h / p.scale;
+        ext_top = (p.band_row0 + p.band_keep_row0 > 0) ? 1 : 0;
+        ext_bot = (p.band_row0 + p.band_keep_row0 + keepn < p.band_global_h) ? 1 : 0;
+        mg.org_y -= ext_top; mg.out_h += ext_top + ext_bot;
+    }
+    const bool staged = out_on_host || ext_top || ext_bot;
+    RUN(mfsr_stage_fallback_upsample(h->rgb_ref, h->rgb_pitch, w, hh, h->fallback, h->out_pitch_own, &mg, st));
     // ---- H+I. fused merge + normalise (+ gamma)
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_MERGE], st));
-    float* dst = out_on_host ? h->outbuf : out;
-    const int64_t dst_pitch = out_on_host ? h->out_pitch_own : out_pitch;
+    float* dst = staged ? h->outbuf : out;
+    const int64_t dst_pitch = staged ? h->out_pitch_own : out_pitch;
     RUN(mfsr_stage_merge(h->rawp, h->rawp_pitch, h->rawp_fs, (const float*)h->mask, h->mask_pitch, h->mask_fs,
                          (const float*)cur, h->flow_pitch, h->flow_fs, (const float*)h->kern, h->kern_pitch,
-                         h->fallback, h->out_pitch_own, dst, dst_pitch, nullptr, nullptr, 0, n, &h->geom, cfa,
+                         h->fallback, h->out_pitch_own, dst, dst_pitch, nullptr, nullptr, 0, n, &mg, cfa,
                          p.white_level, p.black_level, p.weight_threshold, p.merge_flags & ~MFSR_MERGE_NO_FALLBACK, st));
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_DOWNLOAD], st));
-    if (out_on_host)
-        MFSR_CUDA_TRY(cudaMemcpy2DAsync(out, out_pitch, h->outbuf, h->out_pitch_own, (size_t)h->geom.out_w * 12, h->geom.out_h, cudaMemcpyDeviceToHost, st));
+    if (staged)
+        MFSR_CUDA_TRY(cudaMemcpy2DAsync(out, out_pitch, (const char*)h->outbuf + h->out_pitch_own * ext_top, h->out_pitch_own, (size_t)h->geom.out_w * 12,
+                                        h->geom.out_h, out_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_COUNT], st));
     h->ran = true;
     if (out_on_host && sync_host) MFSR_CUDA_TRY(cudaStreamSynchronize(st));

@@ -1,0 +1,126 @@
+"""Row-band sharding of ONE very large burst over the GPUs of a box (BASELINE config 4).
+
+Every rank owns a contiguous band of raw rows of all N frames.  The only exchange step of the path is the halo: the
+rows a band needs from its neighbours so that every stage (coarsest-level tile matching has the largest footprint)
+sees true data around the rows it keeps.  Halo rows travel by NCCL send/recv over NVLink (`exchange_halos`, one grouped
+batch per direction); after that each rank runs the unmodified chain on band + halo in row-band mode
+(`mfsr_params.band_*`), which maps tile rows through the full frame's coordinates and merges only the kept rows.
+No other collective touches the data path.
+
+Band origins are multiples of `tile_size << (levels - 1)` (128 rows by default) so that the tile grids and the 2x2
+pyramid of a band coincide with the full-frame ones; flow-from-tiles and the LK warp evaluate their normalised texture
+coordinates in full-frame coordinates; the merge window grows by one row at interior seams.  The stitched result is
+bit-identical to the single-GPU full-frame result (tests/test_rowband_gpu.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List
+
+import torch
+
+DEFAULT_HALO = 256     # rows; two coarsest-level tiles (2 x 128 rows) cover the matcher's footprint at 4 levels
+
+
+@dataclass(frozen=True)
+class Band:
+    rank: int
+    row0: int        # first owned raw row (global)
+    row1: int        # one past the last owned raw row
+    top: int         # first row of band + halo (global, multiple of the grid)
+    bottom: int      # one past the last row of band + halo
+
+    @property
+    def rows(self) -> int:
+        return self.row1 - self.row0
+
+    @property
+    def halo_up(self) -> int:
+        return self.row0 - self.top
+
+    @property
+    def halo_down(self) -> int:
+        return self.bottom - self.row1
+
+
+def plan_bands(height: int, world: int, grid: int = 128, halo: int = DEFAULT_HALO) -> List[Band]:
+    """Contiguous bands whose origins are multiples of `grid`; the last band takes the remainder."""
+    if height < grid * world:
+        raise ValueError(f"{height} rows cannot be split into {world} bands aligned to {grid}")
+    if halo % grid:
+        raise ValueError("halo must be a multiple of the grid (band + halo origins stay aligned)")
+    units = height // grid
+    base, extra = divmod(units, world)
+    bands, r = [], 0
+    for k in range(world):
+        n = (base + (1 if k < extra else 0)) * grid
+        r1 = height if k == world - 1 else r + n
+        bands.append(Band(k, r, r1, max(0, r - halo), min(height, r1 + halo)))
+        r = r1
+    for b in bands:
+        if world > 1 and (b.halo_up > bands[b.rank - 1].rows if b.rank > 0 else False):
+            raise ValueError("halo larger than a neighbouring band: use fewer ranks or a smaller halo")
+        if world > 1 and b.rank < world - 1 and b.halo_down > bands[b.rank + 1].rows:
+            raise ValueError("halo larger than a neighbouring band: use fewer ranks or a smaller halo")
+    return bands
+
+
+def exchange_halos(own: torch.Tensor, bands: List[Band], rank: int, group=None) -> torch.Tensor:
+    """own: [N, band.rows, W] (the rank's rows of every frame).  Returns [N, band + halo rows, W].
+
+    One send and one receive per neighbour, all posted as a single batch (torch.distributed.batch_isend_irecv ->
+    grouped ncclSend/ncclRecv on NCCL, plain sockets on gloo)."""
+    import torch.distributed as dist
+    b = bands[rank]
+    dtype = own.dtype
+    own = own.contiguous().view(torch.uint8)        # bytes on the wire: every backend moves uint8
+    n, rows, w = own.shape
+    assert rows == b.rows
+    out = torch.empty((n, b.bottom - b.top, w), dtype=own.dtype, device=own.device)
+    out[:, b.halo_up:b.halo_up + rows] = own
+    ops, keep = [], []
+    if rank > 0:                                   # upper neighbour: I need its last halo_up rows, it needs my first rows
+        up = bands[rank - 1]
+        recv = torch.empty((n, b.halo_up, w), dtype=own.dtype, device=own.device)
+        send = own[:, :up.halo_down].contiguous()
+        ops += [dist.P2POp(dist.isend, send, rank - 1, group), dist.P2POp(dist.irecv, recv, rank - 1, group)]
+        keep.append(("up", recv, send))
+    if rank < len(bands) - 1:
+        dn = bands[rank + 1]
+        recv = torch.empty((n, b.halo_down, w), dtype=own.dtype, device=own.device)
+        send = own[:, rows - dn.halo_up:].contiguous()
+        ops += [dist.P2POp(dist.isend, send, rank + 1, group), dist.P2POp(dist.irecv, recv, rank + 1, group)]
+        keep.append(("down", recv, send))
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+    for side, recv, _ in keep:
+        if side == "up":
+            out[:, :b.halo_up] = recv
+        else:
+            out[:, b.halo_up + rows:] = recv
+    return out.view(dtype)
+
+
+def band_params(params, band: Band, global_height: int):
+    """Copy of `params` switched to row-band mode for `band`."""
+    p = type(params).from_buffer_copy(params)
+    p.full_frame = 1
+    p.band_global_h = int(global_height)
+    p.band_row0 = int(band.top)
+    p.band_keep_row0 = int(band.halo_up)
+    p.band_keep_rows = int(band.rows)
+    return p
+
+
+def run_band(params, frames_with_halo: torch.Tensor, band: Band, global_height: int, device: int = 0, ref_idx: int = 0):
+    """Runs the chain on band + halo (CUDA tensor [N, rows, W], 16-bit) and returns the band's output rows [s*rows, s*W, 3]."""
+    from .pipeline import BurstSuperResolution
+    n, h, w = frames_with_halo.shape
+    sr = BurstSuperResolution(band_params(params, band, global_height), device=device, max_width=w, max_height=h, max_frames=n)
+    sr.set_input(frames_with_halo.contiguous(), ref_idx=ref_idx)
+    out = sr.next_frame()
+    sr.synchronize()
+    res = out.clone()
+    sr.close()
+    return res
