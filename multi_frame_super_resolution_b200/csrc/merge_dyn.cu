@@ -133,10 +133,18 @@ __device__ __forceinline__ void pixel_fast(const float (&w)[mt::NW], const float
 
 // 13 regression weights of absolute HR pixel (X, Y) (:401, :427-430) from the staged kernel-parameter window.
 // kwin: float4 [KHS][KWS], origin (kx0, ky0) in raw coordinates, clamp addressing already applied while staging.
-static __device__ __noinline__ void compute_weights(const float4* __restrict__ kwin, int kws, int kx0, int ky0, int X, int Y, float* __restrict__ wl)
+__device__ __forceinline__ float4 lds_f4(unsigned addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// kwin_s: 32-bit SHARED address of the window (a generic pointer would turn the four loads into generic LDs)
+static __device__ __noinline__ void compute_weights(unsigned kwin_s, int kws, int kx0, int ky0, int X, int Y, float* __restrict__ wl)
 {
     const int fx = ((X - 1) >> 1) - kx0, fy = ((Y - 1) >> 1) - ky0;
-    const float4 K00 = kwin[fy * kws + fx], K10 = kwin[fy * kws + fx + 1], K01 = kwin[(fy + 1) * kws + fx], K11 = kwin[(fy + 1) * kws + fx + 1];
+    const unsigned a00 = kwin_s + (unsigned)(fy * kws + fx) * 16u, a01 = a00 + (unsigned)kws * 16u;
+    const float4 K00 = lds_f4(a00), K10 = lds_f4(a00 + 16u), K01 = lds_f4(a01), K11 = lds_f4(a01 + 16u);
     const float ta = (X & 1) ? 0.25f : 0.75f, tb = (Y & 1) ? 0.25f : 0.75f;
     const float kx = tex_mix(K00.x, K10.x, K01.x, K11.x, ta, tb);
     const float ky = tex_mix(K00.y, K10.y, K01.y, K11.y, ta, tb);
@@ -155,40 +163,39 @@ static __device__ __noinline__ void compute_weights(const float4* __restrict__ k
 }
 
 // CFA phase -> colour, ApplyWeighting (kernel.cu:426), GammasRGB (:393), one write of one pixel.
-static __device__ __noinline__ void epilogue_px(const FastArgs& F, int x, int y, float a0, float a1, float a2, float a3,
-                                                float b0, float b1, float b2, float b3, float f0, float f1, float f2)
+// Everything arrives BY VALUE: an out-of-line function can reach the kernel parameters only through a generic pointer
+// (LD through the constant window instead of LDC), which put ~10 dependent generic loads in front of every pixel's store.
+// cfa4: the four CFA colours packed 2 bits each.
+static __device__ __noinline__ void epilogue_px(float* __restrict__ orow, float* __restrict__ so, float* __restrict__ wo, unsigned cfa4, float threshold, int flags,
+                                                float a0, float a1, float a2, float a3, float b0, float b1, float b2, float b3, float f0, float f1, float f2)
 {
-    const MergeArgs& A = F.a;
     const float acc[4] = {a0, a1, a2, a3}, wacc[4] = {b0, b1, b2, b3}, fb3[3] = {f0, f1, f2};
     float s3[3] = {0.f, 0.f, 0.f}, w3[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        const int col = A.cfa.c[q];
+        const unsigned col = (cfa4 >> (2 * q)) & 3u;
 #pragma unroll
         for (int c = 0; c < 3; c++)
-            if (col == c) { s3[c] += acc[q]; w3[c] += wacc[q]; }
+            if (col == (unsigned)c) { s3[c] += acc[q]; w3[c] += wacc[q]; }
     }
-    if (A.sum_out) {
-        float* so = row_ptr(A.sum_out, A.acc_pitch, y) + 3 * x;
-        float* wo = row_ptr(A.weight_out, A.acc_pitch, y) + 3 * x;
+    if (so) {
         so[0] = s3[0]; so[1] = s3[1]; so[2] = s3[2];
         wo[0] = w3[0]; wo[1] = w3[1]; wo[2] = w3[2];
     }
-    float* orow = row_ptr(A.out, A.out_pitch, y) + 3 * x;
 #pragma unroll
-    for (int c = 0; c < 3; c++) orow[c] = finish_px(apply_weighting(s3[c], w3[c], fb3[c], A.threshold), A.flags);
+    for (int c = 0; c < 3; c++) orow[c] = finish_px(apply_weighting(s3[c], w3[c], fb3[c], threshold), flags);
 }
 
 // 3x3 normalised raw samples around (k, ky) of an alignment outlier whose window is not staged, from global memory.
 // No clamping: the caller has checked that every tap stays inside the clamp range.
-static __device__ __noinline__ void fetch_raw_global(const FastArgs& F, int f, int k, int ky, float* __restrict__ out9)
+// rawf: frame base, norm_s: 32-bit SHARED address of {black[4], 1/white[4]} per CFA phase (by value / shared for the same
+// reason as epilogue_px: no generic loads of kernel parameters on this path).
+static __device__ __noinline__ void fetch_raw_global(const uint16_t* __restrict__ rawf, int64_t raw_pitch, unsigned norm_s, int k, int ky, float* __restrict__ out9)
 {
-    const MergeArgs& A = F.a;
-    const uint16_t* raw = (const uint16_t*)((const char*)A.raw + A.raw_fs * f);
     unsigned v[9];
 #pragma unroll
     for (int r = 0; r < 3; r++) {
-        const uint16_t* rrow = row_ptr(raw, A.raw_pitch, ky - 1 + r) + (k - 1);
+        const uint16_t* rrow = row_ptr(rawf, raw_pitch, ky - 1 + r) + (k - 1);
 #pragma unroll
         for (int c = 0; c < 3; c++) v[r * 3 + c] = __ldg(rrow + c);
     }
@@ -197,7 +204,10 @@ static __device__ __noinline__ void fetch_raw_global(const FastArgs& F, int f, i
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const int ph = ((ky - 1 + r) & 1) * 2 + ((k - 1 + c) & 1);
-            out9[r * 3 + c] = ((float)v[r * 3 + c] - F.black_ph[ph]) * F.inv_ph[ph];
+            float bl, iv;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bl) : "r"(norm_s + 4u * ph));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(iv) : "r"(norm_s + 16u + 4u * ph));
+            out9[r * 3 + c] = ((float)v[r * 3 + c] - bl) * iv;
         }
 }
 
@@ -210,7 +220,7 @@ static __device__ __noinline__ void slow_pixel(const FastArgs& F, int f, int X, 
 
 // One pass of one warp: tile row `row` (absolute Y % 4 == YM), the 32 pixels X = X0abs + 4*lane + J.
 template <int TH, int YM, int J>
-__device__ __forceinline__ void run_row(const FastArgs& F, const unsigned char* smem, const int2* fbase, int row, int x0, int y0, int X0abs, int Y0abs)
+__device__ __forceinline__ void run_row(const FastArgs& F, const unsigned char* smem, const int2* fbase, unsigned norm_s, int row, int x0, int y0, int X0abs, int Y0abs)
 {
     using C = DCfg<TH>;
     const MergeArgs& A = F.a;
@@ -231,7 +241,7 @@ __device__ __forceinline__ void run_row(const FastArgs& F, const unsigned char* 
     if (pix_on) {
         // ---- regression weights, frame independent (shared out-of-line code; wl doubles as the slow path's copy)
         float wl[mt::NW], W[mt::NW];
-        compute_weights((const float4*)(smem + (size_t)N * C::FRAME_BYTES), C::KWS, (X0abs >> 1) - 1, (Y0abs >> 1) - 1, X, Y, wl);
+        compute_weights((unsigned)__cvta_generic_to_shared(smem + (size_t)N * C::FRAME_BYTES), C::KWS, (X0abs >> 1) - 1, (Y0abs >> 1) - 1, X, Y, wl);
 #pragma unroll
         for (int i = 0; i < mt::NW; i++) W[i] = wl[i];
         // a pixel-frame runs the staged path when none of its taps (shifted or not) touches the clamp range (:414-419)
@@ -264,7 +274,7 @@ __device__ __forceinline__ void run_row(const FastArgs& F, const unsigned char* 
                     for (int r = 0; r < 3; r++) { R[r][0] = pe[r * RWS]; R[r][1] = po[r * RWS]; R[r][2] = pe[r * RWS + 1]; }
                 } else {                                   // alignment outlier: its window is not staged
                     float tmp[9];
-                    fetch_raw_global(F, f, k, ky, tmp);
+                    fetch_raw_global((const uint16_t*)((const char*)A.raw + A.raw_fs * f), A.raw_pitch, norm_s, k, ky, tmp);
 #pragma unroll
                     for (int r = 0; r < 3; r++) { R[r][0] = tmp[3 * r]; R[r][1] = tmp[3 * r + 1]; R[r][2] = tmp[3 * r + 2]; }
                 }
@@ -281,16 +291,19 @@ __device__ __forceinline__ void run_row(const FastArgs& F, const unsigned char* 
         }
     }
 
-    epilogue_px(F, x, y, acc[0], acc[1], acc[2], acc[3], wacc[0], wacc[1], wacc[2], wacc[3], fb3[0], fb3[1], fb3[2]);
+    const unsigned cfa4 = (unsigned)A.cfa.c[0] | ((unsigned)A.cfa.c[1] << 2) | ((unsigned)A.cfa.c[2] << 4) | ((unsigned)A.cfa.c[3] << 6);
+    epilogue_px(row_ptr(A.out, A.out_pitch, y) + 3 * x, A.sum_out ? row_ptr(A.sum_out, A.acc_pitch, y) + 3 * x : nullptr,
+                A.sum_out ? row_ptr(A.weight_out, A.acc_pitch, y) + 3 * x : nullptr, cfa4, A.threshold, A.flags,
+                acc[0], acc[1], acc[2], acc[3], wacc[0], wacc[1], wacc[2], wacc[3], fb3[0], fb3[1], fb3[2]);
 }
 
 template <int TH, int YM>
-__device__ __forceinline__ void run_rows(const FastArgs& F, const unsigned char* smem, const int2* fbase, int row, int x0, int y0, int X0abs, int Y0abs)
+__device__ __forceinline__ void run_rows(const FastArgs& F, const unsigned char* smem, const int2* fbase, unsigned norm_s, int row, int x0, int y0, int X0abs, int Y0abs)
 {
-    run_row<TH, YM, 0>(F, smem, fbase, row, x0, y0, X0abs, Y0abs);
-    run_row<TH, YM, 1>(F, smem, fbase, row, x0, y0, X0abs, Y0abs);
-    run_row<TH, YM, 2>(F, smem, fbase, row, x0, y0, X0abs, Y0abs);
-    run_row<TH, YM, 3>(F, smem, fbase, row, x0, y0, X0abs, Y0abs);
+    run_row<TH, YM, 0>(F, smem, fbase, norm_s, row, x0, y0, X0abs, Y0abs);
+    run_row<TH, YM, 1>(F, smem, fbase, norm_s, row, x0, y0, X0abs, Y0abs);
+    run_row<TH, YM, 2>(F, smem, fbase, norm_s, row, x0, y0, X0abs, Y0abs);
+    run_row<TH, YM, 3>(F, smem, fbase, norm_s, row, x0, y0, X0abs, Y0abs);
 }
 
 template <int TH>
@@ -301,6 +314,9 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int2 fbase[MAXF];           // origin (rx0, ry0) of the staged raw window per frame
     __shared__ int s_part[MAXF * (TH / 2)][3];   // per (frame, row pair) item: sum sx, sum sy, count of sampled (non-outsized) shifts
+    __shared__ float s_norm[8];            // black level [4] and reciprocal white level [4] per CFA phase, for the out-of-line outlier fetch
+    if (threadIdx.x < 8) s_norm[threadIdx.x] = threadIdx.x < 4 ? F.black_ph[threadIdx.x] : F.inv_ph[threadIdx.x - 4];
+    const unsigned norm_s = (unsigned)__cvta_generic_to_shared(s_norm);
     const MergeArgs& A = F.a;
     const mfsr_merge_geom& g = A.g;
     const int N = A.n_frames;
@@ -486,10 +502,10 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
     // ---------------- phase 2: warp w owns tile row w (Y % 4 == w % 4 == its scheduler): four passes J = 0..3,
     // each a small loop over the frames (one code variant per warp scheduler at any time)
     switch (warp & 3) {
-        case 0: run_rows<TH, 0>(F, smem, fbase, warp, x0, y0, X0abs, Y0abs); break;
-        case 1: run_rows<TH, 1>(F, smem, fbase, warp, x0, y0, X0abs, Y0abs); break;
-        case 2: run_rows<TH, 2>(F, smem, fbase, warp, x0, y0, X0abs, Y0abs); break;
-        default: run_rows<TH, 3>(F, smem, fbase, warp, x0, y0, X0abs, Y0abs); break;
+        case 0: run_rows<TH, 0>(F, smem, fbase, norm_s, warp, x0, y0, X0abs, Y0abs); break;
+        case 1: run_rows<TH, 1>(F, smem, fbase, norm_s, warp, x0, y0, X0abs, Y0abs); break;
+        case 2: run_rows<TH, 2>(F, smem, fbase, norm_s, warp, x0, y0, X0abs, Y0abs); break;
+        default: run_rows<TH, 3>(F, smem, fbase, norm_s, warp, x0, y0, X0abs, Y0abs); break;
     }
 }
 
