@@ -91,7 +91,7 @@ __device__ __forceinline__ bool lk_pinv(float a, float b, float c, float d, floa
 // thread in the window sums) executed 1170 instructions per pixel at 82 % issue utilisation (profiles/r1j_lk_ncu.txt).
 //   W region (source + warped): tile + HW + 2 on each side      R region (derivatives): tile + HW
 template <int HW>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov, int64_t img_pitch,
                     const float2* __restrict__ flow_in, float2* __restrict__ flow_out, int64_t flow_pitch,
                     int w, int h, float minDet, int gh, int gy0)
@@ -228,11 +228,14 @@ lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov
                 }
         }
         if (gx < w) {
+            float2 fin[4];                     // the four flow values are requested before the first pseudo-inverse
+#pragma unroll
+            for (int p = 0; p < 4; p++) fin[p] = __ldg(flow_in + (size_t)(min(y0 + ly0 + p, h - 1) * pf + gx));
 #pragma unroll
             for (int p = 0; p < 4; p++) {
                 const int gy = y0 + ly0 + p;
                 if (gy >= h) break;
-                float2 f = __ldg(row_ptr(flow_in, flow_pitch, gy) + gx);
+                float2 f = fin[p];
                 if (!(gx < HW || gx >= w - HW || gy < HW || gy >= h - HW)) {
                     float inv[4];
                     if (lk_pinv(acc[p][0], acc[p][1], acc[p][1], acc[p][2], minDet, inv)) {
