@@ -282,9 +282,13 @@ extern "C" int mfsr_set_frames(mfsr_handle h, const void* const* frames, int n, 
     if (in_place) {
         h->rawp = (const uint16_t*)frames[0]; h->rawp_pitch = pitch; h->rawp_fs = stride;
     } else {
-        for (int f = 0; f < n; f++)
-            MFSR_CUDA_TRY(cudaMemcpy2DAsync((char*)h->raw + h->raw_fs * f, h->raw_pitch, frames[f], pitch, (size_t)width * 2, height,
-                                            on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+        // dense rows on both sides: one linear copy per frame (the 2-D form is not guaranteed to collapse to it)
+        const bool dense = pitch == (int64_t)width * 2 && h->raw_pitch == pitch;
+        for (int f = 0; f < n; f++) {
+            const cudaMemcpyKind kind = on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+            if (dense) MFSR_CUDA_TRY(cudaMemcpyAsync((char*)h->raw + h->raw_fs * f, frames[f], (size_t)pitch * height, kind, h->stream));
+            else MFSR_CUDA_TRY(cudaMemcpy2DAsync((char*)h->raw + h->raw_fs * f, h->raw_pitch, frames[f], pitch, (size_t)width * 2, height, kind, h->stream));
+        }
         h->rawp = h->raw; h->rawp_pitch = h->raw_pitch; h->rawp_fs = h->raw_fs;
     }
     h->have_frames = true; h->ran = false;
@@ -422,9 +426,12 @@ static int run_impl(mfsr_handle h, float* out, int64_t out_pitch, int out_on_hos
                          h->fallback, h->out_pitch_own, dst, dst_pitch, nullptr, nullptr, 0, n, &mg, cfa,
                          p.white_level, p.black_level, p.weight_threshold, p.merge_flags & ~MFSR_MERGE_NO_FALLBACK, st));
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_DOWNLOAD], st));
-    if (staged)
-        MFSR_CUDA_TRY(cudaMemcpy2DAsync(out, out_pitch, (const char*)h->outbuf + h->out_pitch_own * ext_top, h->out_pitch_own, (size_t)h->geom.out_w * 12,
-                                        h->geom.out_h, out_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+    if (staged) {
+        const cudaMemcpyKind kind = out_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+        const char* src = (const char*)h->outbuf + h->out_pitch_own * ext_top;
+        if (out_pitch == h->out_pitch_own) MFSR_CUDA_TRY(cudaMemcpyAsync(out, src, (size_t)out_pitch * h->geom.out_h, kind, st));
+        else MFSR_CUDA_TRY(cudaMemcpy2DAsync(out, out_pitch, src, h->out_pitch_own, (size_t)h->geom.out_w * 12, h->geom.out_h, kind, st));
+    }
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_COUNT], st));
     h->ran = true;
     if (out_on_host && sync_host) MFSR_CUDA_TRY(cudaStreamSynchronize(st));
