@@ -115,9 +115,13 @@ typedef struct mfsr_params {
      * rows [band_row0, band_row0 + height) of a burst that is band_global_h rows tall; only output rows
      * s*[band_keep_row0, band_keep_row0 + band_keep_rows) (LOCAL raw rows) are produced.  band_row0 must be a
      * multiple of tile_size << (levels - 1) so that the tile and pyramid grids coincide with the full-frame ones;
-     * base_rotation must be 0.  All zero = not a band. */
+     * base_rotation must be 0.  All zero = not a band.
+     * band_margin > 0: the per-pixel stages (flow, kernel parameters, robustness) run only on the kept rows +- band_margin
+     * rows instead of the whole band + halo (the wide halo is needed by the coarse pyramid levels of the tile matcher only);
+     * it must cover the stencil footprints plus the largest vertical flow: 15 + 12 + max |flow_y| rows.  0 = whole band. */
     int   band_global_h, band_row0, band_keep_row0, band_keep_rows;
-    int   reserved[4];
+    int   band_margin;
+    int   reserved[3];
 } mfsr_params;
 
 int         mfsr_abi_version(void);

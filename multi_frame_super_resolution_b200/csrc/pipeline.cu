@@ -129,7 +129,7 @@ static int validate_params(const mfsr_params* p)
     if (p->lk_iterations < 0 || p->lk_half_window < 1 || p->lk_half_window > 4) return MFSR_E_INVALID;
     if (p->tensor_box_radius < 0 || p->tensor_box_radius > 3 || p->mask_erode_radius < 0 || p->mask_erode_radius > 8) return MFSR_E_INVALID;
     for (int i = 0; i < 4; i++) if (p->cfa[i] < 0 || p->cfa[i] > 2) return MFSR_E_INVALID;
-    if (p->band_global_h < 0 || p->band_row0 < 0 || p->band_keep_row0 < 0 || p->band_keep_rows < 0) return MFSR_E_INVALID;
+    if (p->band_global_h < 0 || p->band_row0 < 0 || p->band_keep_row0 < 0 || p->band_keep_rows < 0 || p->band_margin < 0) return MFSR_E_INVALID;
     if (p->band_global_h > 0) {
         const int grid = p->tile_size << (p->levels - 1);
         if (!p->full_frame || p->base_rotation != 0.0f || (p->band_row0 % grid) || p->band_row0 >= p->band_global_h) return MFSR_E_INVALID;
@@ -373,32 +373,49 @@ static int run_impl(mfsr_handle h, float* out, int64_t out_pitch, int out_on_hos
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_FLOW], st));
     float2* cur = h->flowA; float2* nxt = h->flowB;
     const int gh = p.band_global_h, gty = gh > 0 ? (gh - 2 * p.max_shift) / p.tile_size : 0;
+    // Row-band mode with band_margin > 0: the per-pixel stages (flow, kernel parameters, robustness) only run on the kept
+    // rows + margin, rows [ra, rb) of the band; the wide halo is only needed by the pyramid tile matcher.  Every kernel
+    // below is a stencil with clamp addressing whose footprint (LK: 5 rows per sweep + |flow|) stays inside the margin for
+    // the kept rows, so the kept rows' values do not change (tests/test_rowband_gpu.py checks bit-identity).
+    int ra = 0, rb = hh;
+    if (gh > 0 && p.band_margin > 0) {
+        const int keepn = p.band_keep_rows > 0 ? p.band_keep_rows : hh - p.band_keep_row0;
+        ra = (p.band_keep_row0 - p.band_margin) & ~1; if (ra < 0) ra = 0;
+        rb = (p.band_keep_row0 + keepn + p.band_margin + 1) & ~1; if (rb > hh) rb = hh;
+    }
+    const int rh = rb - ra, gy0 = p.band_row0 + ra;
     for (int f = 0; f < n; f++)
-        RUN(launch_flow_from_tiles(h->frame_shift + (size_t)f * nt, (int64_t)tx * 8, tx, ty, (float2*)((char*)cur + h->flow_fs * f), h->flow_pitch,
-                                   w, hh, p.base_shift[0], p.base_shift[1], p.base_rotation, gh, p.band_row0, gty, p.band_row0 / p.tile_size, st));
+        RUN(launch_flow_from_tiles(h->frame_shift + (size_t)f * nt, (int64_t)tx * 8, tx, ty,
+                                   (float2*)((char*)cur + h->flow_fs * f + h->flow_pitch * ra), h->flow_pitch,
+                                   w, rh, p.base_shift[0], p.base_shift[1], p.base_rotation, gh, gy0, gty, p.band_row0 / p.tile_size, st));
     for (int it = 0; it < p.lk_iterations; it++) {
         for (int f = 0; f < n; f++) {
             if (f == h->ref_idx) {   // reference against itself: Iz == 0 -> UV == 0, flow unchanged
-                MFSR_CUDA_TRY(cudaMemcpyAsync((char*)nxt + h->flow_fs * f, (char*)cur + h->flow_fs * f, h->flow_fs, cudaMemcpyDeviceToDevice, st));
+                MFSR_CUDA_TRY(cudaMemcpyAsync((char*)nxt + h->flow_fs * f + h->flow_pitch * ra, (char*)cur + h->flow_fs * f + h->flow_pitch * ra,
+                                              (size_t)h->flow_pitch * rh, cudaMemcpyDeviceToDevice, st));
                 continue;
             }
-            RUN(launch_lk_iteration((const float*)((const char*)h->gray + h->gray_fs * h->ref_idx), (const float*)((const char*)h->gray + h->gray_fs * f),
-                                    h->gray_pitch, (const float2*)((const char*)cur + h->flow_fs * f), (float2*)((char*)nxt + h->flow_fs * f),
-                                    h->flow_pitch, w, hh, p.lk_half_window, p.lk_min_det, gh, p.band_row0, st));
+            RUN(launch_lk_iteration((const float*)((const char*)h->gray + h->gray_fs * h->ref_idx + h->gray_pitch * ra),
+                                    (const float*)((const char*)h->gray + h->gray_fs * f + h->gray_pitch * ra), h->gray_pitch,
+                                    (const float2*)((const char*)cur + h->flow_fs * f + h->flow_pitch * ra),
+                                    (float2*)((char*)nxt + h->flow_fs * f + h->flow_pitch * ra),
+                                    h->flow_pitch, w, rh, p.lk_half_window, p.lk_min_det, gh, gy0, st));
         }
         float2* t = cur; cur = nxt; nxt = t;
     }
     h->flow_final = cur;
     // ---- F. merge kernel parameters from the reference frame
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_KERNEL], st));
-    RUN(mfsr_stage_kernel_params((const float*)((const char*)h->gray + h->gray_fs * h->ref_idx), h->gray_pitch, (float*)h->kern, h->kern_pitch,
-                                 w, hh, p.tensor_box_radius, p.Dth, p.Dtr, p.kDetail, p.kDenoise, p.kStretch, p.kShrink, st));
+    RUN(mfsr_stage_kernel_params((const float*)((const char*)h->gray + h->gray_fs * h->ref_idx + h->gray_pitch * ra), h->gray_pitch,
+                                 (float*)((char*)h->kern + h->kern_pitch * ra), h->kern_pitch,
+                                 w, rh, p.tensor_box_radius, p.Dth, p.Dtr, p.kDetail, p.kDenoise, p.kStretch, p.kShrink, st));
     // ---- G. robustness masks
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_ROBUST], st));
     for (int f = 0; f < n; f++) {
-        RUN(mfsr_stage_robustness((const float*)((const char*)h->rgb_half + h->rgbh_fs * h->ref_idx), (const float*)((const char*)h->rgb_half + h->rgbh_fs * f),
-                                  h->rgbh_pitch, (const float*)((const char*)cur + h->flow_fs * f), h->flow_pitch,
-                                  (float*)((char*)h->mask + h->mask_fs * f), h->mask_pitch, (float*)h->mask_tmp, hw2, hh2,
+        RUN(mfsr_stage_robustness((const float*)((const char*)h->rgb_half + h->rgbh_fs * h->ref_idx + h->rgbh_pitch * (ra / 2)),
+                                  (const float*)((const char*)h->rgb_half + h->rgbh_fs * f + h->rgbh_pitch * (ra / 2)),
+                                  h->rgbh_pitch, (const float*)((const char*)cur + h->flow_fs * f + h->flow_pitch * ra), h->flow_pitch,
+                                  (float*)((char*)h->mask + h->mask_fs * f + h->mask_pitch * (ra / 2)), h->mask_pitch, (float*)h->mask_tmp, hw2, rh / 2,
                                   p.alpha, p.beta, p.thresholdM, p.mask_erode_radius, st));
         if (p.mask_erode_radius > 0) h->launches += 2;
     }

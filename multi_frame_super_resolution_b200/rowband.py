@@ -20,6 +20,8 @@ from typing import List
 import torch
 
 DEFAULT_HALO = 256     # rows; two coarsest-level tiles (2 x 128 rows) cover the matcher's footprint at 4 levels
+DEFAULT_MARGIN = 64    # rows beyond the kept rows on which flow / kernel parameters / robustness are evaluated (mfsr_params.band_margin):
+                       # stencil footprints (LK 3 x 5 rows, robustness 12) + vertical flows up to ~35 rows
 
 
 @dataclass(frozen=True)
@@ -102,9 +104,10 @@ def exchange_halos(own: torch.Tensor, bands: List[Band], rank: int, group=None) 
     return out.view(dtype)
 
 
-def band_params(params, band: Band, global_height: int):
-    """Copy of `params` switched to row-band mode for `band`."""
+def band_params(params, band: Band, global_height: int, margin: int = DEFAULT_MARGIN):
+    """Copy of `params` switched to row-band mode for `band`.  margin = 0 evaluates every stage on the whole band + halo."""
     p = type(params).from_buffer_copy(params)
+    p.band_margin = int(margin)
     p.full_frame = 1
     p.band_global_h = int(global_height)
     p.band_row0 = int(band.top)

@@ -13,8 +13,8 @@ from multi_frame_super_resolution_b200.synth import synth_burst
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_bands_reproduce_full_frame(cuda_device, world):
+@pytest.mark.parametrize("world,margin", [(2, 64), (3, 64), (3, 0), (2, 32)])
+def test_bands_reproduce_full_frame(cuda_device, world, margin):
     n, h, w = 4, 1152, 512
     fr, _ = synth_burst(n, h, w, seed=11)
     p = default_params()
@@ -27,7 +27,7 @@ def test_bands_reproduce_full_frame(cuda_device, world):
     bands = rowband.plan_bands(h, world, 128, 256)
     out = np.empty_like(full)
     for b in bands:
-        bp = rowband.band_params(p, b, h)
+        bp = rowband.band_params(p, b, h, margin)
         srb = BurstSuperResolution(bp, 0, w, b.bottom - b.top, n)
         srb.set_input(dev[:, b.top:b.bottom].contiguous())
         got = srb.next_frame().cpu().numpy()

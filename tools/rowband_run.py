@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--height", type=int, default=6048); ap.add_argument("--width", type=int, default=8064)
     ap.add_argument("--frames", type=int, default=15); ap.add_argument("--halo", type=int, default=rowband.DEFAULT_HALO)
     ap.add_argument("--steps", type=int, default=3); ap.add_argument("--verify", action="store_true")
+    ap.add_argument("--margin", type=int, default=rowband.DEFAULT_MARGIN)
     a = ap.parse_args()
     rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
@@ -36,7 +37,7 @@ def main():
     if not a.verify:
         del full
     torch.cuda.synchronize(dev)
-    bp = rowband.band_params(p, b, a.height)
+    bp = rowband.band_params(p, b, a.height, a.margin)
     sr = BurstSuperResolution(bp, device=lr, max_width=a.width, max_height=b.bottom - b.top, max_frames=a.frames)
     ow, oh = sr.output_size(a.width, b.bottom - b.top)
     out = torch.empty((oh, ow, 3), dtype=torch.float32, device=dev)
@@ -61,7 +62,7 @@ def main():
     ms = sum(x[0] for x in times) / len(times); ms_halo = sum(x[1] for x in times) / len(times)
     line = {"workload": f"{a.width}x{a.height} x {a.frames} frames, 2x, row bands", "n_gpus": world, "ms_per_burst": round(ms, 2),
             "ms_halo_exchange": round(ms_halo, 3), "output_megapixels_per_second": round(4 * a.width * a.height / 1e6 / (ms / 1e3), 1),
-            "halo_rows": a.halo, "halo_bytes_per_rank": int((b.halo_up + b.halo_down) * a.width * 2 * a.frames),
+            "halo_rows": a.halo, "margin_rows": a.margin, "halo_bytes_per_rank": int((b.halo_up + b.halo_down) * a.width * 2 * a.frames),
             "band_rows": [x.rows for x in bands], "processed_rows": [x.bottom - x.top for x in bands]}
     if a.verify:
         stitched = None
