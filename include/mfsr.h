@@ -70,6 +70,10 @@ extern "C" {
 #define MFSR_FMT_GRAY_U16  1    /* monochrome: cfa = {G,G,G,G}, channel .y     */
 
 /* Flags for mfsr_stage_merge / mfsr_params.merge_flags */
+#define MFSR_OUT_F32 0           /* output formats of mfsr_run_format */
+#define MFSR_OUT_F16 1
+#define MFSR_OUT_U8  2
+
 #define MFSR_MERGE_GAMMA        1   /* apply GammasRGB (kernel.cu:393) in the epilogue     */
 #define MFSR_MERGE_NO_FALLBACK  2   /* `fallback` is NULL: treat as all-zero reference img */
 
@@ -312,6 +316,11 @@ int mfsr_run(mfsr_handle h, float* out, int64_t out_pitch, int out_on_host);
  * mfsr_synchronize(h) before reading it or re-using the handle's frames.  Two handles driven alternately
  * overlap one burst's PCIe transfers with the other's kernels (the way bench.py measures `e2e`). */
 int mfsr_run_async(mfsr_handle h, float* out, int64_t out_pitch, int out_on_host);
+/* Same chain, result delivered in `out_format`: MFSR_OUT_F32 (float3, identical to mfsr_run), MFSR_OUT_F16 (half3, round to
+ * nearest: within 2.5e-4 of the float image on [0,1]) or MFSR_OUT_U8 (floor(v*255+0.5) saturated, the 8-bit image the reference
+ * program writes after GammasRGB, multi_frame_sr.cpp:207 — set MFSR_MERGE_GAMMA in merge_flags for sRGB coding).  `out_pitch`
+ * in bytes of the chosen format.  async != 0 behaves like mfsr_run_async.  Cuts the D2H volume of a host result 2x / 4x. */
+int mfsr_run_format(mfsr_handle h, void* out, int64_t out_pitch, int out_on_host, int out_format, int async);
 int mfsr_synchronize(mfsr_handle h);
 void* mfsr_stream(mfsr_handle h);
 

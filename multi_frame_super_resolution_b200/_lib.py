@@ -92,6 +92,7 @@ SIGNATURES = {
     "mfsr_set_frames": (c_i, [vp, C.POINTER(vp), c_i, c_i, c_i, c_i64, c_i, c_i, c_i]),
     "mfsr_run": (c_i, [vp, vp, c_i64, c_i]),
     "mfsr_run_async": (c_i, [vp, vp, c_i64, c_i]),
+    "mfsr_run_format": (c_i, [vp, vp, c_i64, c_i, c_i, c_i]),
     "mfsr_synchronize": (c_i, [vp]),
     "mfsr_stream": (vp, [vp]),
     "mfsr_get_tile_grid": (c_i, [vp, ip, ip, ip]),

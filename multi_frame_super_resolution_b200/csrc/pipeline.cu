@@ -6,6 +6,7 @@
 // allocation, status codes instead of silent failure.
 #include "common.cuh"
 #include "internal.h"
+#include <cuda_fp16.h>
 #include <new>
 #include <string.h>
 #include <vector>
@@ -51,6 +52,23 @@ struct mfsr_context {
     float2* flow_final;   // which of flowA/flowB holds the final flow
     mfsr_merge_geom geom;
 };
+
+// float3 image -> the caller's output format (mfsr_run_format): two floats per thread over the dense image.
+// F16: round-to-nearest-even halves.  U8: floor(v * 255 + 0.5) saturated, NaN -> 0 (what the reference program writes to its PNGs
+// after GammasRGB, multi_frame_sr.cpp:207).
+template <int FMT>
+__global__ void __launch_bounds__(256)
+convert_out_kernel(const float2* __restrict__ in, void* __restrict__ out, int64_t n2)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    const float2 v = __ldg(in + i);
+    if (FMT == MFSR_OUT_F16) ((__half2*)out)[i] = __floats2half2_rn(v.x, v.y);
+    else {
+        const float a = fminf(fmaxf(floorf(v.x * 255.0f + 0.5f), 0.0f), 255.0f), b = fminf(fmaxf(floorf(v.y * 255.0f + 0.5f), 0.0f), 255.0f);
+        ((uchar2*)out)[i] = make_uchar2((unsigned char)(a == a ? a : 0.0f), (unsigned char)(b == b ? b : 0.0f));
+    }
+}
 
 static void make_geom(const mfsr_params& p, int w, int h, mfsr_merge_geom* g)
 {
@@ -297,14 +315,20 @@ extern "C" int mfsr_set_frames(mfsr_handle h, const void* const* frames, int n, 
 
 #define RUN(expr) do { int _rc = (expr); if (_rc) return _rc; h->launches++; } while (0)
 
-static int run_impl(mfsr_handle h, float* out, int64_t out_pitch, int out_on_host, bool sync_host);
+static int run_impl(mfsr_handle h, void* out, int64_t out_pitch, int out_on_host, bool sync_host, int out_format);
 
-extern "C" int mfsr_run(mfsr_handle h, float* out, int64_t out_pitch, int out_on_host) { return run_impl(h, out, out_pitch, out_on_host, true); }
-extern "C" int mfsr_run_async(mfsr_handle h, float* out, int64_t out_pitch, int out_on_host) { return run_impl(h, out, out_pitch, out_on_host, false); }
-
-static int run_impl(mfsr_handle h, float* out, int64_t out_pitch, int out_on_host, bool sync_host)
+extern "C" int mfsr_run(mfsr_handle h, float* out, int64_t out_pitch, int out_on_host) { return run_impl(h, out, out_pitch, out_on_host, true, MFSR_OUT_F32); }
+extern "C" int mfsr_run_async(mfsr_handle h, float* out, int64_t out_pitch, int out_on_host) { return run_impl(h, out, out_pitch, out_on_host, false, MFSR_OUT_F32); }
+extern "C" int mfsr_run_format(mfsr_handle h, void* out, int64_t out_pitch, int out_on_host, int out_format, int async)
 {
+    return run_impl(h, out, out_pitch, out_on_host, !async, out_format);
+}
+
+static int run_impl(mfsr_handle h, void* out_any, int64_t out_pitch, int out_on_host, bool sync_host, int out_format)
+{
+    float* out = (float*)out_any;
     if (!h || !out) return MFSR_E_INVALID;
+    if (out_format != MFSR_OUT_F32 && out_format != MFSR_OUT_F16 && out_format != MFSR_OUT_U8) return MFSR_E_INVALID;
     if (!h->have_frames) return MFSR_E_STATE;
     MFSR_CUDA_TRY(cudaSetDevice(h->device));
     const mfsr_params& p = h->p;
@@ -432,7 +456,7 @@ static int run_impl(mfsr_handle h, float* out, int64_t out_pitch, int out_on_hos
         ext_bot = (p.band_row0 + p.band_keep_row0 + keepn < p.band_global_h) ? 1 : 0;
         mg.org_y -= ext_top; mg.out_h += ext_top + ext_bot;
     }
-    const bool staged = out_on_host || ext_top || ext_bot;
+    const bool staged = out_on_host || ext_top || ext_bot || out_format != MFSR_OUT_F32;
     RUN(mfsr_stage_fallback_upsample(h->rgb_ref, h->rgb_pitch, w, hh, h->fallback, h->out_pitch_own, &mg, st));
     // ---- H+I. fused merge + normalise (+ gamma)
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_MERGE], st));
@@ -446,8 +470,21 @@ static int run_impl(mfsr_handle h, float* out, int64_t out_pitch, int out_on_hos
     if (staged) {
         const cudaMemcpyKind kind = out_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
         const char* src = (const char*)h->outbuf + h->out_pitch_own * ext_top;
-        if (out_pitch == h->out_pitch_own) MFSR_CUDA_TRY(cudaMemcpyAsync(out, src, (size_t)out_pitch * h->geom.out_h, kind, st));
-        else MFSR_CUDA_TRY(cudaMemcpy2DAsync(out, out_pitch, src, h->out_pitch_own, (size_t)h->geom.out_w * 12, h->geom.out_h, kind, st));
+        int64_t src_pitch = h->out_pitch_own, row_bytes = (int64_t)h->geom.out_w * 12;
+        if (out_format != MFSR_OUT_F32) {
+            // converted image goes into the (now dead) fallback buffer, dense rows
+            const int64_t n2 = (int64_t)h->geom.out_w * h->geom.out_h * 3 / 2;
+            const unsigned blocks = (unsigned)((n2 + 255) / 256);
+            if (out_format == MFSR_OUT_F16) convert_out_kernel<MFSR_OUT_F16><<<blocks, 256, 0, st>>>((const float2*)src, h->fallback, n2);
+            else convert_out_kernel<MFSR_OUT_U8><<<blocks, 256, 0, st>>>((const float2*)src, h->fallback, n2);
+            MFSR_LAUNCH_CHECK();
+            h->launches++;
+            const int bpp = out_format == MFSR_OUT_F16 ? 6 : 3;
+            src = (const char*)h->fallback; src_pitch = row_bytes = (int64_t)h->geom.out_w * bpp;
+        }
+        if (out_pitch < row_bytes) return MFSR_E_INVALID;
+        if (out_pitch == src_pitch) MFSR_CUDA_TRY(cudaMemcpyAsync(out, src, (size_t)out_pitch * h->geom.out_h, kind, st));
+        else MFSR_CUDA_TRY(cudaMemcpy2DAsync(out, out_pitch, src, src_pitch, (size_t)row_bytes, h->geom.out_h, kind, st));
     }
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_COUNT], st));
     h->ran = true;

@@ -19,6 +19,7 @@ from ._lib import Params, check
 
 FMT_BAYER_U16 = 0
 FMT_GRAY_U16 = 1
+OUT_F32, OUT_F16, OUT_U8 = 0, 1, 2
 
 _cudart = None
 
@@ -136,11 +137,25 @@ class BurstSuperResolution:
         self._keep = frames          # the async H2D copies read it until the stream reaches them
 
     # -- nextFrame: run the whole chain, return the float3 image
-    def next_frame(self, out=None, host: bool = False, sync: bool = True):
-        """host=True: `out` is host memory; sync=False only enqueues the D2H copy (pinned `out`), call synchronize()."""
+    def next_frame(self, out=None, host: bool = False, sync: bool = True, dtype: torch.dtype = torch.float32):
+        """host=True: `out` is host memory; sync=False only enqueues the D2H copy (pinned `out`), call synchronize().
+        dtype: torch.float32 (mfsr_run), torch.float16 or torch.uint8 (mfsr_run_format: half3 / 8-bit image)."""
         if self._shape is None:
             raise RuntimeError("set_input() first")
         ow, oh = self.output_size(self._shape[1], self._shape[0])
+        if dtype != torch.float32:
+            fmt = {torch.float16: OUT_F16, torch.uint8: OUT_U8}[dtype]
+            if out is None:
+                out = torch.empty((oh, ow, 3), dtype=dtype, pin_memory=True) if host else torch.empty((oh, ow, 3), dtype=dtype, device=f"cuda:{self.device}")
+            if out.dtype != dtype or tuple(out.shape) != (oh, ow, 3) or not out.is_contiguous():
+                raise ValueError("out must be a contiguous [out_h, out_w, 3] tensor of the requested dtype")
+            check(self._lib.mfsr_run_format(self._h, C.c_void_p(out.data_ptr()), ow * 3 * out.element_size(), 1 if host else 0, fmt, 0 if (sync and host) else 1),
+                  "mfsr_run_format")
+            if host:
+                self._keep_out = out
+            else:
+                torch.cuda.current_stream(self.device).wait_stream(self._ext())
+            return out
         if host:
             if out is None:
                 out = torch.empty((oh, ow, 3), dtype=torch.float32, pin_memory=True)

@@ -145,3 +145,30 @@ def test_pipeline_async_two_handles(cuda_device):
         assert np.array_equal(outs[i].numpy(), ref[i]), i
     for hd in hs:
         hd.close()
+
+
+def test_output_formats(cuda_device):
+    """mfsr_run_format: the half3 image is the float image rounded to nearest, the 8-bit image is floor(v*255+.5) saturated
+    (what the reference program writes to its PNGs, multi_frame_sr.cpp:207); device and host delivery agree."""
+    p = default_params()
+    p.levels = 3
+    p.merge_flags = 1                     # GammasRGB, like the reference's 8-bit result
+    fr, _ = synth_burst(4, 192, 256, seed=5)
+    sr = BurstSuperResolution(p, 0, 256, 192, 4)
+    sr.set_input(fr.to(cuda_device))
+    f32 = sr.next_frame().clone()
+    f16 = sr.next_frame(dtype=torch.float16).clone()
+    u8 = sr.next_frame(dtype=torch.uint8).clone()
+    u8_host = sr.next_frame(host=True, dtype=torch.uint8)
+    f16_host = sr.next_frame(host=True, sync=False, dtype=torch.float16)
+    sr.synchronize()
+    assert torch.equal(f16, f32.half())
+    assert float((f16.float() - f32).abs().max()) <= 2.5e-4
+    exp8 = torch.clamp(torch.floor(torch.nan_to_num(f32) * 255.0 + 0.5), 0, 255).to(torch.uint8)
+    assert torch.equal(u8, exp8)
+    assert torch.equal(u8_host, exp8.cpu()) and torch.equal(f16_host, f16.cpu())
+    lib = sr._lib
+    import ctypes as C
+    assert lib.mfsr_run_format(sr._h, C.c_void_p(u8.data_ptr()), 256 * 2 * 3, 0, 7, 0) == -1          # unknown format
+    assert lib.mfsr_run_format(sr._h, C.c_void_p(u8.data_ptr()), 10, 0, 2, 0) == -1                   # pitch below a row
+    sr.close()
