@@ -157,8 +157,11 @@ lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov
 #pragma unroll
                 for (int k = 0; k < CNT; k++)
                     if (ok[k]) {
-                        s_src[ly[k]][lx] = srcv[k];
-                        s_wrp[ly[k]][lx] = tex_mix(t00[k], t10[k], t01[k], t11[k], fa[k], fb[k]);
+                        // the derivative stencil is linear: ((D src) / 12 + (D warped) / 12) / 2 == D(src + warped) / 24, and
+                        // Iz = warped - src, so the sum and the difference are what the next step needs
+                        const float wv = tex_mix(t00[k], t10[k], t01[k], t11[k], fa[k], fb[k]);
+                        s_src[ly[k]][lx] = srcv[k] + wv;
+                        s_wrp[ly[k]][lx] = wv - srcv[k];
                     }
             };
             constexpr int WB = 4;
@@ -168,22 +171,29 @@ lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov
         }
     }
     __syncthreads();
-    // 2. derivatives (ComputeDerivativesKernel, :97): 5-tap (1,-8,0,8,-1)/12 on source and warped.  Region elements were
-    // loaded at CLAMPED image coordinates, so plain local neighbours equal the reference's clamp addressing for every
+    // 2. derivatives (ComputeDerivativesKernel, :97): 5-tap (1,-8,0,8,-1)/12 on source and warped, averaged == the same stencil
+    // on (source + warped) / 24 (s_src holds the sum, s_wrp the difference; re-associated, tolerance-checked).  Region elements
+    // were loaded at CLAMPED image coordinates, so plain local neighbours equal the reference's clamp addressing for every
     // element inside the image; elements outside the image are never read by a valid output (:205-207 skips the border).
-    for (int i = tid; i < RW * RH; i += NT) {
-        const int ry = i / RW, rx = i - ry * RW;
+    // Two horizontally adjacent outputs per thread (aligned float2 loads: WW, RW and the region origin are even).
+    static_assert(WW % 2 == 0 && RW % 2 == 0, "float2 access");
+    for (int i = tid; i < (RW / 2) * RH; i += NT) {
+        const int ry = i / (RW / 2), rx = (i - ry * (RW / 2)) * 2;
         const int cy = ry + 2, cx = rx + 2;
-        float t0, t1;
-        t0 = s_src[cy][cx + 2]; t0 -= s_src[cy][cx + 1] * 8.0f; t0 += s_src[cy][cx - 1] * 8.0f; t0 -= s_src[cy][cx - 2]; t0 *= (1.0f / 12.0f);
-        t1 = s_wrp[cy][cx + 2]; t1 -= s_wrp[cy][cx + 1] * 8.0f; t1 += s_wrp[cy][cx - 1] * 8.0f; t1 -= s_wrp[cy][cx - 2]; t1 *= (1.0f / 12.0f);
-        s_ix[ry][rx] = (t0 + t1) * 0.5f;
-        // texSource = warped, texTarget = reference: the stencil above is MINUS the derivative, so Iz = warped - ref is
+        const float2 a = *(const float2*)&s_src[cy][cx - 2], b = *(const float2*)&s_src[cy][cx], c = *(const float2*)&s_src[cy][cx + 2];
+        float2 ix;
+        // texSource = warped, texTarget = reference: the stencil below is MINUS the derivative, so Iz = warped - ref is
         // the sign that makes `shift += UV` descend (restated host)
-        s_it[ry][rx] = s_wrp[cy][cx] - s_src[cy][cx];
-        t0 = s_src[cy + 2][cx]; t0 -= s_src[cy + 1][cx] * 8.0f; t0 += s_src[cy - 1][cx] * 8.0f; t0 -= s_src[cy - 2][cx]; t0 *= (1.0f / 12.0f);
-        t1 = s_wrp[cy + 2][cx]; t1 -= s_wrp[cy + 1][cx] * 8.0f; t1 += s_wrp[cy - 1][cx] * 8.0f; t1 -= s_wrp[cy - 2][cx]; t1 *= (1.0f / 12.0f);
-        s_iy[ry][rx] = (t0 + t1) * 0.5f;
+        ix.x = (c.x - b.y * 8.0f + a.y * 8.0f - a.x) * (1.0f / 24.0f);
+        ix.y = (c.y - c.x * 8.0f + b.x * 8.0f - a.y) * (1.0f / 24.0f);
+        *(float2*)&s_ix[ry][rx] = ix;
+        *(float2*)&s_it[ry][rx] = *(const float2*)&s_wrp[cy][cx];
+        const float2 u2 = *(const float2*)&s_src[cy - 2][cx], u1 = *(const float2*)&s_src[cy - 1][cx];
+        const float2 d1 = *(const float2*)&s_src[cy + 1][cx], d2 = *(const float2*)&s_src[cy + 2][cx];
+        float2 iy;
+        iy.x = (d2.x - d1.x * 8.0f + u1.x * 8.0f - u2.x) * (1.0f / 24.0f);
+        iy.y = (d2.y - d1.y * 8.0f + u1.y * 8.0f - u2.y) * (1.0f / 24.0f);
+        *(float2*)&s_iy[ry][rx] = iy;
     }
     __syncthreads();
     // 3. row sums of the five products over [-HW, HW]: two adjacent outputs per thread share 2*HW+2 taps (LDS.64)
@@ -210,22 +220,22 @@ lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov
     // 4. column sums, pseudo-inverse, update (lucasKanadeOptim, :190): 4 vertically adjacent pixels per thread
     {
         const int lx = threadIdx.x, ly0 = threadIdx.y * 4, gx = x0 + lx;
+        // the four windows [p, p + 2 HW] share the rows 3 .. 2 HW and pairs of their edge rows: 13 additions per quantity
+        // instead of 24
         float acc[4][5];
 #pragma unroll
-        for (int p = 0; p < 4; p++)
+        for (int q = 0; q < 5; q++) {
+            float v[2 * HW + 4];
 #pragma unroll
-            for (int q = 0; q < 5; q++) acc[p][q] = 0.f;
+            for (int r = 0; r < 2 * HW + 4; r++) v[r] = s_h[q][ly0 + r][lx];
+            float core = 0.f;
 #pragma unroll
-        for (int r = 0; r < 2 * HW + 4; r++) {
-            float v[5];
-#pragma unroll
-            for (int q = 0; q < 5; q++) v[q] = s_h[q][ly0 + r][lx];
-#pragma unroll
-            for (int p = 0; p < 4; p++)
-                if (r >= p && r <= p + 2 * HW) {
-#pragma unroll
-                    for (int q = 0; q < 5; q++) acc[p][q] += v[q];
-                }
+            for (int r = 3; r <= 2 * HW; r++) core = (r == 3) ? v[r] : core + v[r];
+            const float lo = v[1] + v[2], hi = v[2 * HW + 1] + v[2 * HW + 2];
+            acc[0][q] = (v[0] + lo) + core;
+            acc[1][q] = (lo + v[2 * HW + 1]) + core;
+            acc[2][q] = (v[2] + hi) + core;
+            acc[3][q] = (hi + v[2 * HW + 3]) + core;
         }
         if (gx < w) {
             float2 fin[4];                     // the four flow values are requested before the first pseudo-inverse
