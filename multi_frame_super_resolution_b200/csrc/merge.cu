@@ -15,6 +15,9 @@
 
 namespace mfsr {
 
+// S: compile-time scale (1..4; 0 = read it from the geometry).  With a runtime scale every tap pays four integer divisions
+// (~80 of ~90 instructions per tap); as a template constant they are multiply-shift sequences.
+template <int S>
 __global__ void __launch_bounds__(256)
 merge_generic_kernel(const __grid_constant__ MergeArgs A)
 {
@@ -24,7 +27,7 @@ merge_generic_kernel(const __grid_constant__ MergeArgs A)
     if (x >= g.out_w || y >= g.out_h) return;
 
     float acc[3] = {0.f, 0.f, 0.f}, wacc[3] = {0.f, 0.f, 0.f};
-    const int s = g.scale;
+    const int s = S ? S : g.scale;
     // the reference skips the 1-px border of the output window (DeBayerKernels.cu:391)
     const bool interior = !(x < 1 || y < 1 || x >= g.out_w - 1 || y >= g.out_h - 1);
     if (interior) {
@@ -75,13 +78,14 @@ merge_generic_kernel(const __grid_constant__ MergeArgs A)
                     const float4 m = __ldg(mrow + (ppx / 2));
                     float cert = col == 0 ? m.x : (col == 1 ? m.y : m.z);
                     if (!isfinite(cert)) cert = 0.0f;
+                    // one division per tap (the colour only selects its operands), same expression order as the reference
+                    const float bl = col == 0 ? A.black[0] : (col == 1 ? A.black[1] : A.black[2]);
+                    const float wh = col == 0 ? A.white[0] : (col == 1 ? A.white[1] : A.white[2]);
+                    const float rn = (r - bl) / wh;
+                    const float v = rn * wt * cert, wv = wt * cert;
 #pragma unroll
                     for (int c = 0; c < 3; c++)
-                        if (col == c) {
-                            const float rn = (r - A.black[c]) / A.white[c];
-                            acc[c] += rn * wt * cert;
-                            wacc[c] += wt * cert;
-                        }
+                        if (col == c) { acc[c] += v; wacc[c] += wv; }
                 }
             }
         }
@@ -143,7 +147,13 @@ extern "C" int mfsr_stage_merge(const uint16_t* raw, int64_t raw_pitch, int64_t 
         if (rc != MFSR_E_INVALID) return rc;
     }
     dim3 block(32, 8), grid(cdiv(geom->out_w, 32), cdiv(geom->out_h, 8));
-    merge_generic_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(A);
+    switch (geom->scale) {
+        case 1: merge_generic_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(A); break;
+        case 2: merge_generic_kernel<2><<<grid, block, 0, (cudaStream_t)stream>>>(A); break;
+        case 3: merge_generic_kernel<3><<<grid, block, 0, (cudaStream_t)stream>>>(A); break;
+        case 4: merge_generic_kernel<4><<<grid, block, 0, (cudaStream_t)stream>>>(A); break;
+        default: merge_generic_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(A); break;
+    }
     MFSR_LAUNCH_CHECK();
     return MFSR_OK;
 }

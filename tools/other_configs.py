@@ -1,0 +1,17 @@
+import sys, torch
+sys.path.insert(0, '.')
+from multi_frame_super_resolution_b200.pipeline import BurstSuperResolution, default_params
+from multi_frame_super_resolution_b200.synth import synth_burst
+dev = torch.device('cuda', 0)
+for (name, n, h, w, scale, ms, fmt) in (('config5 4K x30 3x', 30, 2160, 3840, 3, 48.0, 0), ('config3 1080p gray x8 2x', 8, 1080, 1920, 2, 3.0, 1)):
+    p = default_params(); p.scale = scale
+    sr = BurstSuperResolution(p, device=0, max_width=w, max_height=h, max_frames=n)
+    fr, sh = synth_burst(n, h, w, seed=7, device=dev, max_shift=ms)
+    ow, oh = sr.output_size(w, h)
+    out = torch.empty((oh, ow, 3), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        sr.set_input(fr, fmt=fmt); sr.next_frame(out=out)
+    torch.cuda.synchronize()
+    st = sr.stage_ms()
+    print(name, {k: round(v, 2) for k, v in st.items()}, 'sum', round(sum(st.values()), 2), 'MP/s', round(ow * oh / 1e6 / (sum(st.values()) / 1e3)), flush=True)
+    sr.close(); del fr, out
