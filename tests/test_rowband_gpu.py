@@ -41,3 +41,28 @@ def test_bands_reproduce_full_frame(cuda_device, world, margin):
             assert np.array_equal(ts[t0 - off:t1 - off], full_shift[f][t0:t1]), (b, f)
         srb.close()
     assert np.array_equal(out, full), f"{(out != full).mean():.2e} of samples differ, max {np.abs(out - full).max():.3g}"
+
+
+def test_full_size_determinism_and_band_equivalence(cuda_device):
+    """Size-independent properties at BASELINE config 2's full size (4032x3024 x 8 frames, 2x): (1) two runs of the chain
+    are bit-identical (the merge is a gather: no atomics, no run-to-run ordering); (2) two row bands stitched reproduce the
+    full-frame image bit for bit."""
+    n, h, w = 8, 3024, 4032
+    fr, _ = synth_burst(n, h, w, seed=1234, device=cuda_device)
+    p = default_params()
+    sr = BurstSuperResolution(p, 0, w, h, n)
+    sr.set_input(fr)
+    a = sr.next_frame().clone()
+    sr.set_input(fr)
+    b = sr.next_frame()
+    assert torch.equal(a, b)
+    assert bool(torch.isfinite(a).all()) and 0.2 < float(a.mean()) < 0.8
+    sr.close()
+    del b
+    bands = rowband.plan_bands(h, 2, 128, 256)
+    for bd in bands:
+        srb = BurstSuperResolution(rowband.band_params(p, bd, h), 0, w, bd.bottom - bd.top, n)
+        srb.set_input(fr[:, bd.top:bd.bottom].contiguous())
+        got = srb.next_frame()
+        assert torch.equal(got, a[2 * bd.row0:2 * bd.row1]), bd
+        srb.close()
