@@ -1,0 +1,245 @@
+// multi_frame_sr_b200 — C++ host of the B200 burst super-resolution path, over the C ABI of include/mfsr.h only
+// (no CUDA headers, no torch): what a maintainer of the reference gets by swapping the cv::superres block of
+// finalProject/Project/multi_frame_sr.cpp:165-203 for libmfsr_b200.so.
+//
+//   ./multi_frame_sr_b200 optFlowName inputName iterations          (multi_frame_sr.cpp:122-144: same three arguments)
+//
+// * inputName city / car / iso select the reference's frame sets (:151-163) with Netpbm files instead of PNG/JPEG — this image
+//   has no OpenCV C++ to decode those: img_%06d.{pgm,ppm} (5), car/%d.{pgm,ppm} (4), iso/%06d.{pgm,ppm} (4), numbered from 1
+//   like the reference (from 0 is tried too: the repository ships img_000000..4).  Any other inputName is a printf pattern
+//   and needs a 4th argument: the number of frames.
+//   P5 (maxval > 255: 16-bit big-endian) = Bayer RGGB or gray raw frames, used as they are; P6 8-bit colour frames are
+//   mosaiced to RGGB on the 10-bit range of the default parameters (raw = round(v * 959 / 255) + 64).
+// * optFlowName is accepted and echoed into the output names (:207-209); the burst path has its own aligner, `iterations`
+//   sets its Lucas-Kanade sweeps (:181 setIterations).
+// * like the reference, the burst is processed num_times = 10 times and the last real_times = 5 are timed (:146-149,:188-203);
+//   prints "<t> sec" and "<fps> FPS" (:204-205), writes <input>_<flow>_sr_result.ppm and the sharpened _sr2_result.ppm (:206-209).
+#include "mfsr.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct RawFrame {
+    int w = 0, h = 0;
+    bool gray = false;                 // P5 8-bit input: monochrome, kept as gray
+    std::vector<uint16_t> px;          // dense rows
+};
+
+bool next_token(FILE* f, std::string& tok)
+{
+    tok.clear();
+    int c;
+    while ((c = fgetc(f)) != EOF) {
+        if (c == '#') { while ((c = fgetc(f)) != EOF && c != '\n') {} continue; }
+        if (c == ' ' || c == '\t' || c == '\n' || c == '\r') { if (!tok.empty()) return true; continue; }
+        tok.push_back((char)c);
+    }
+    return !tok.empty();
+}
+
+// Netpbm P5 / P6 -> 16-bit raw frame (see the header comment for the mapping)
+bool load_frame(const std::string& path, RawFrame& out)
+{
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    std::string magic, sw, sh, smax;
+    bool ok = next_token(f, magic) && next_token(f, sw) && next_token(f, sh) && next_token(f, smax);
+    const int w = ok ? atoi(sw.c_str()) : 0, h = ok ? atoi(sh.c_str()) : 0, maxv = ok ? atoi(smax.c_str()) : 0;
+    ok = ok && w > 0 && h > 0 && maxv > 0 && maxv < 65536 && (magic == "P5" || magic == "P6");
+    if (!ok) { fclose(f); return false; }
+    const int ch = magic == "P6" ? 3 : 1, bps = maxv > 255 ? 2 : 1;
+    std::vector<unsigned char> buf((size_t)w * h * ch * bps);
+    ok = fread(buf.data(), 1, buf.size(), f) == buf.size();
+    fclose(f);
+    if (!ok) return false;
+    const int ew = w & ~1, eh = h & ~1;          // the path wants even dimensions
+    out.w = ew; out.h = eh; out.gray = false;
+    out.px.assign((size_t)ew * eh, 0);
+    auto sample = [&](int x, int y, int c) -> int {
+        const size_t i = ((size_t)y * w + x) * ch + c;
+        return bps == 2 ? (buf[2 * i] << 8) | buf[2 * i + 1] : buf[i];
+    };
+    for (int y = 0; y < eh; y++)
+        for (int x = 0; x < ew; x++) {
+            int v;
+            if (ch == 1 && bps == 2) v = sample(x, y, 0);                                    // raw frame as it is
+            else {
+                const int c = ch == 1 ? 0 : ((y & 1) ? ((x & 1) ? 2 : 1) : ((x & 1) ? 1 : 0));   // RGGB: R G / G B
+                v = (int)std::floor(sample(x, y, c) * 959.0 / maxv + 0.5) + 64;
+            }
+            out.px[(size_t)y * ew + x] = (uint16_t)v;
+        }
+    out.gray = (ch == 1 && bps == 1);
+    return true;
+}
+
+bool write_ppm(const std::string& path, const std::vector<unsigned char>& rgb, int w, int h)
+{
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    fprintf(f, "P6\n%d %d\n255\n", w, h);
+    const bool ok = fwrite(rgb.data(), 1, rgb.size(), f) == rgb.size();
+    fclose(f);
+    return ok;
+}
+
+// sharpenImg2 (multi_frame_sr.cpp:90-119): 5 c - left - right - up - down, saturated; the reference advances its output pointer
+// from the START of the row while reading from column 1, so the result sits one pixel to the left; border rows / columns are 0
+// (the one column the reference leaves uninitialised is 0 here).
+std::vector<unsigned char> sharpen(const std::vector<unsigned char>& img, int w, int h)
+{
+    std::vector<unsigned char> out(img.size(), 0);
+    const int ch = 3, row = w * ch;
+    for (int y = 1; y < h - 1; y++) {
+        const unsigned char* cur = &img[(size_t)y * row];
+        unsigned char* o = &out[(size_t)y * row];
+        for (int col = ch; col < (w - 1) * ch; col++) {
+            const int v = 5 * cur[col] - cur[col - ch] - cur[col + ch] - cur[col - row] - cur[col + row];
+            *o++ = (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+        for (int c = 0; c < ch; c++) { out[(size_t)y * row + c] = 0; out[(size_t)y * row + (w - 1) * ch + c] = 0; }
+    }
+    return out;
+}
+
+// The pull-style source of the reference (MultiFrameSource_CUDA, multi_frame_sr.cpp:18-49): hands out one frame per call,
+// nullptr when exhausted, reset() rewinds.
+class BurstFrameSource {
+public:
+    explicit BurstFrameSource(std::vector<RawFrame> frames) : frames_(std::move(frames)) {}
+    const RawFrame* nextFrame() { return index_ < frames_.size() ? &frames_[index_++] : nullptr; }
+    void reset() { index_ = 0; }
+    size_t size() const { return frames_.size(); }
+private:
+    size_t index_ = 0;
+    std::vector<RawFrame> frames_;
+};
+
+// The slice of cv::superres::SuperResolution the reference program uses (:179-194), on top of one mfsr handle.
+class BurstSuperResolution {
+public:
+    ~BurstSuperResolution() { if (h_) mfsr_destroy(h_); }
+    void setScale(int s) { scale_ = s; }
+    void setIterations(int it) { iterations_ = it; }
+    void setInput(BurstFrameSource* src) { src_ = src; }
+    int outWidth() const { return ow_; }
+    int outHeight() const { return oh_; }
+    // pulls the whole burst from the source (temporal area = the burst) and produces the 8-bit sRGB image
+    int nextFrame(std::vector<unsigned char>& result)
+    {
+        if (!src_) return MFSR_E_STATE;
+        src_->reset();
+        std::vector<const void*> ptrs;
+        const RawFrame* first = nullptr;
+        while (const RawFrame* f = src_->nextFrame()) {
+            if (!first) first = f;
+            if (f->w != first->w || f->h != first->h) return MFSR_E_INVALID;
+            ptrs.push_back(f->px.data());
+        }
+        if (!first) return MFSR_E_INVALID;
+        if (!h_) {
+            mfsr_params p;
+            mfsr_default_params(&p);
+            p.scale = scale_; p.lk_iterations = iterations_; p.merge_flags = MFSR_MERGE_GAMMA;
+            while (p.levels > 1 && (std::min(first->w, first->h) >> (p.levels - 1)) < 2 * p.max_shift + p.tile_size) p.levels--;
+            const int rc = mfsr_create(&p, 0, first->w, first->h, (int)ptrs.size(), &h_);
+            if (rc) return rc;
+            mfsr_output_size(h_, first->w, first->h, &ow_, &oh_);
+        }
+        int rc = mfsr_set_frames(h_, ptrs.data(), (int)ptrs.size(), first->w, first->h, (int64_t)first->w * 2,
+                                 first->gray ? MFSR_FMT_GRAY_U16 : MFSR_FMT_BAYER_U16, 0, /*on_host*/1);
+        if (rc) return rc;
+        result.resize((size_t)ow_ * oh_ * 3);
+        return mfsr_run_format(h_, result.data(), (int64_t)ow_ * 3, /*out_on_host*/1, MFSR_OUT_U8, /*async*/0);
+    }
+private:
+    mfsr_handle h_ = nullptr;
+    BurstFrameSource* src_ = nullptr;
+    int scale_ = 2, iterations_ = 3, ow_ = 0, oh_ = 0;
+};
+
+void usage()
+{
+    printf("./multi_frame_sr_b200 optFlowName inputName iterations [frames]\n");
+    printf("\toptFlowName: farneback, tvl1, brox, pyrlk (accepted for compatibility)\n");
+    printf("\tinputName: city, car, iso, or a printf pattern of .pgm/.ppm frames with [frames]\n");
+    printf("\titerations: integer, 1, 10, etc.\n");
+}
+
+}  // namespace
+
+int main(int argc, char** argv)
+{
+    std::string flow = "farneback", input = "city";
+    int iterations = 10, n_override = 0;
+    if (argc == 4 || argc == 5) {
+        flow = argv[1]; input = argv[2]; iterations = atoi(argv[3]);
+        if (iterations < 1) iterations = 1;
+        if (argc == 5) n_override = atoi(argv[4]);
+    } else if (argc != 1) {
+        usage();
+        return -1;
+    }
+    const int scale = 2, num_times = 10, real_times = 5;
+    int num_images;
+    std::string pattern, tag = input;
+    if (input == "city") { num_images = 5; pattern = "img_%06d"; }
+    else if (input == "car") { num_images = 4; pattern = "car/%d"; }
+    else if (input == "iso") { num_images = 4; pattern = "iso/%06d"; }
+    else if (n_override > 0) { num_images = n_override; pattern = input; tag = "burst"; }
+    else { printf("wrong input\n"); return -1; }
+
+    std::vector<RawFrame> frames;
+    char buf[4096];
+    for (int base = 1; base >= 0 && frames.empty(); base--) {
+        for (int i = 0; i < num_images; i++) {
+            RawFrame fr;
+            bool ok = false;
+            for (const char* ext : {"", ".pgm", ".ppm"}) {
+                snprintf(buf, sizeof buf, (pattern + ext).c_str(), i + base);
+                if ((ok = load_frame(buf, fr))) break;
+            }
+            if (!ok) { frames.clear(); break; }
+            printf("%s, [%d x %d]\n", buf, fr.w, fr.h);
+            frames.push_back(std::move(fr));
+        }
+    }
+    if (frames.empty()) {
+        snprintf(buf, sizeof buf, pattern.c_str(), 1);
+        printf("cannot read %s(.pgm|.ppm)\n", buf);
+        return -1;
+    }
+    BurstFrameSource source(std::move(frames));
+    BurstSuperResolution sr;
+    sr.setScale(scale);
+    sr.setIterations(iterations);
+    sr.setInput(&source);
+    std::vector<unsigned char> result;
+    std::chrono::steady_clock::time_point t0;
+    for (int t = 0; t < num_times; t++) {
+        if (t == num_times - real_times) t0 = std::chrono::steady_clock::now();
+        const int rc = sr.nextFrame(result);
+        if (rc) { fprintf(stderr, "mfsr: %s (%d)\n", mfsr_error_string(rc), rc); return 1; }
+    }
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    printf("%g sec\n", sec);
+    printf("%g FPS\n", (double)(real_times * num_images) / sec);
+    const int ow = sr.outWidth(), oh = sr.outHeight();
+    if (!write_ppm(tag + "_" + flow + "_sr_result.ppm", result, ow, oh) ||
+        !write_ppm(tag + "_" + flow + "_sr2_result.ppm", sharpen(result, ow, oh), ow, oh)) {
+        fprintf(stderr, "cannot write the result images\n");
+        return 1;
+    }
+    printf("{\"output_megapixels_per_second\": %.2f, \"frames\": %d, \"out\": [%d, %d], \"scale\": %d, \"lk_iterations\": %d}\n",
+           real_times * (double)ow * oh / 1e6 / sec, num_images, ow, oh, scale, iterations);
+    return 0;
+}

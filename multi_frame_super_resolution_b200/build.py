@@ -79,5 +79,24 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+HOST_SRC = ROOT / "host" / "multi_frame_sr_b200.cpp"
+HOST_BIN = ROOT / "host" / "multi_frame_sr_b200"
+
+
+def build_host(force: bool = False) -> Path:
+    """g++ build of the C++ host program (host/multi_frame_sr_b200.cpp): links the C ABI only, no CUDA headers."""
+    lib = build()
+    if not force and HOST_BIN.exists() and HOST_BIN.stat().st_mtime >= max(HOST_SRC.stat().st_mtime, lib.stat().st_mtime):
+        return HOST_BIN
+    cxx = os.environ.get("CXX", "g++")
+    cuda_lib = str(Path(NVCC).resolve().parent.parent / "lib64")
+    cmd = [cxx, "-O2", "-std=c++17", "-Wall", str(HOST_SRC), "-I", str(ROOT / "include"), "-L", str(PKG), "-lmfsr_b200",
+           "-L", cuda_lib, "-lcudart", "-Wl,-rpath,$ORIGIN/../multi_frame_super_resolution_b200", f"-Wl,-rpath,{cuda_lib}",
+           "-o", str(HOST_BIN)]
+    subprocess.check_call(cmd)
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))

@@ -13,6 +13,7 @@ Mirrors finalProject/Project/multi_frame_sr.cpp:122-209:
 * scale 2, the burst is processed `num_times = 10` times and the last `real_times = 5` repetitions are timed (:146-149);
   prints "<t> sec" and "<fps> FPS" (:204-206), writes <input>_<flow>_sr_result.png and the Laplacian-sharpened
   <input>_<flow>_sr2_result.png (:90-119, :207-209), plus one JSON line with MP/s.
+  (`host/multi_frame_sr_b200.cpp` is the same program in C++ over the C ABI, with Netpbm files.)
 
 8-bit colour frames are mosaiced to RGGB and mapped to the 10-bit range of the default parameters
 (raw = round(v8 * 959 / 255) + 64), exactly like tests/golden/make_bundled_fixture.py.
@@ -40,10 +41,17 @@ def _mosaic_rggb(bgr: np.ndarray) -> np.ndarray:
 
 
 def _sharpen(img8: np.ndarray) -> np.ndarray:
-    """sharpenImg2 (multi_frame_sr.cpp:90-119): img - 0.5 * Laplacian, saturated."""
-    import cv2
-    lap = cv2.Laplacian(img8.astype(np.float32), cv2.CV_32F, ksize=3)
-    return np.clip(img8.astype(np.float32) - 0.5 * lap, 0, 255).astype(np.uint8)
+    """sharpenImg2 (multi_frame_sr.cpp:90-119): 5 c - left - right - up - down, saturated.  The reference advances its output
+    pointer from the START of each row while reading from column 1, so the result sits one pixel to the left; border rows and
+    columns are 0 (the one column the reference leaves uninitialised is 0 here).  Same arithmetic as host/multi_frame_sr_b200.cpp."""
+    a = img8.astype(np.int32)
+    h, w = a.shape[:2]
+    out = np.zeros_like(img8)
+    v = 5 * a[1:-1, 1:-1] - a[1:-1, :-2] - a[1:-1, 2:] - a[:-2, 1:-1] - a[2:, 1:-1]
+    out[1:-1, 0:w - 2] = np.clip(v, 0, 255).astype(np.uint8)
+    out[:, 0] = 0
+    out[:, w - 1] = 0
+    return out
 
 
 def main(argv=None) -> int:
