@@ -25,7 +25,7 @@ FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
     "--expt-relaxed-constexpr", "--extended-lambda",
     "-I", str(ROOT / "include"),
-]
+] + os.environ.get("MFSR_NVCC_EXTRA", "").split()      # e.g. -DMFSR_LOOP_UNROLL=2 for same-box A/B builds (tools/ab_build.sh)
 
 
 # Files whose fp32 results feed discrete decisions (quantisation, arg-min, rounding of tile
