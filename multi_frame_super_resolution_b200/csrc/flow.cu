@@ -14,26 +14,33 @@ namespace mfsr {
 
 // CreateFlowFieldFromTiles (opticalFlow.cu:48-93).  Band form: see internal.h (gh == h, gy0 == 0, gty == tilesY, trow0 == 0
 // for a whole frame).
+constexpr int FFT_ROWS = 8;      // rows per thread: the column-only part (texture column, weights, rotation terms) is computed once
 __global__ void __launch_bounds__(256)
 flow_from_tiles_kernel(const float2* __restrict__ tiles, int64_t tile_pitch, int tilesX, int tilesY,
                        float2* __restrict__ flow, int64_t flow_pitch, int w, int h, float bsx, float bsy, float cr, float sr,
                        int gh, int gy0, int gty, int trow0)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-    float sx = cr * -bsx - sr * -bsy;
-    float sy = sr * -bsx + cr * -bsy;
-    const float pcx = (float)(x - w / 2), pcy = (float)(y + gy0 - gh / 2);
-    sx += cr * pcx - sr * pcy - pcx;
-    sy += sr * pcx + cr * pcy - pcy;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, yb = (blockIdx.y * blockDim.y + threadIdx.y) * FFT_ROWS;
+    if (x >= w || yb >= h) return;
+    const float bx = cr * -bsx - sr * -bsy, by = sr * -bsx + cr * -bsy;
+    const float pcx = (float)(x - w / 2);
     const TexAxis ax = tex_axis(tex_coord((float)x + 0.5f, w, tilesX), tilesX);
-    TexAxis ay = tex_axis(tex_coord((float)(y + gy0) + 0.5f, gh, gty), gty);
-    ay.i0 = clampi(ay.i0 - trow0, 0, tilesY - 1); ay.i1 = clampi(ay.i1 - trow0, 0, tilesY - 1);
-    const float2 t00 = row_ptr(tiles, tile_pitch, ay.i0)[ax.i0], t10 = row_ptr(tiles, tile_pitch, ay.i0)[ax.i1];
-    const float2 t01 = row_ptr(tiles, tile_pitch, ay.i1)[ax.i0], t11 = row_ptr(tiles, tile_pitch, ay.i1)[ax.i1];
-    sx += tex_mix(t00.x, t10.x, t01.x, t11.x, ax.a, ay.a);
-    sy += tex_mix(t00.y, t10.y, t01.y, t11.y, ax.a, ay.a);
-    row_ptr(flow, flow_pitch, y)[x] = make_float2(sx, sy);
+#pragma unroll 2
+    for (int r = 0; r < FFT_ROWS; r++) {
+        const int y = yb + r;
+        if (y >= h) break;
+        float sx = bx, sy = by;
+        const float pcy = (float)(y + gy0 - gh / 2);
+        sx += cr * pcx - sr * pcy - pcx;
+        sy += sr * pcx + cr * pcy - pcy;
+        TexAxis ay = tex_axis(tex_coord((float)(y + gy0) + 0.5f, gh, gty), gty);
+        ay.i0 = clampi(ay.i0 - trow0, 0, tilesY - 1); ay.i1 = clampi(ay.i1 - trow0, 0, tilesY - 1);
+        const float2 t00 = row_ptr(tiles, tile_pitch, ay.i0)[ax.i0], t10 = row_ptr(tiles, tile_pitch, ay.i0)[ax.i1];
+        const float2 t01 = row_ptr(tiles, tile_pitch, ay.i1)[ax.i0], t11 = row_ptr(tiles, tile_pitch, ay.i1)[ax.i1];
+        sx += tex_mix(t00.x, t10.x, t01.x, t11.x, ax.a, ay.a);
+        sy += tex_mix(t00.y, t10.y, t01.y, t11.y, ax.a, ay.a);
+        row_ptr(flow, flow_pitch, y)[x] = make_float2(sx, sy);
+    }
 }
 
 constexpr int LTW = 32, LTH = 32, LHW_MAX = 4;          // output tile of one CTA (256 threads)
@@ -271,7 +278,7 @@ int mfsr::launch_flow_from_tiles(const float2* tiles, int64_t tile_pitch, int ti
 {
     if (!tiles || !flow || tilesX < 1 || tilesY < 1 || w < 1 || h < 1) return MFSR_E_INVALID;
     if (gh <= 0) { gh = h; gy0 = 0; gty = tilesY; tile_row0 = 0; }
-    dim3 b(32, 8), g(cdiv(w, 32), cdiv(h, 8));
+    dim3 b(32, 8), g(cdiv(w, 32), cdiv(h, 8 * FFT_ROWS));
     flow_from_tiles_kernel<<<g, b, 0, st>>>(tiles, tile_pitch, tilesX, tilesY, flow, flow_pitch, w, h, bsx, bsy, cosf(rot), sinf(rot), gh, gy0, gty, tile_row0);
     MFSR_LAUNCH_CHECK();
     return MFSR_OK;

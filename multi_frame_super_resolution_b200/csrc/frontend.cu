@@ -407,20 +407,28 @@ pyramid_down_kernel(const uint8_t* __restrict__ in, int64_t in_pitch, uint8_t* _
 }
 
 // ---------------------------------------------------------------- fallback upsample
+constexpr int FBU_ROWS = 8;      // output rows per thread: the column part (texture column, fraction, source offsets) is computed once
 __global__ void __launch_bounds__(256)
 fallback_upsample_kernel(const float* __restrict__ rgb, int64_t rgb_pitch, int w, int h,
                          float* __restrict__ out, int64_t out_pitch, mfsr_merge_geom g)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= g.out_w || y >= g.out_h) return;
-    const float u = __fdiv_rn((float)(x + g.org_x) + 0.5f, (float)g.scale), v = __fdiv_rn((float)(y + g.org_y) + 0.5f, (float)g.scale);
-    const TexAxis tx = tex_axis(u, w), ty = tex_axis(v, h);
-    const float* r0 = row_ptr(rgb, rgb_pitch, ty.i0);
-    const float* r1 = row_ptr(rgb, rgb_pitch, ty.i1);
-    float* o = row_ptr(out, out_pitch, y) + 3 * x;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, yb = (blockIdx.y * blockDim.y + threadIdx.y) * FBU_ROWS;
+    if (x >= g.out_w || yb >= g.out_h) return;
+    const float fs = (float)g.scale;
+    const TexAxis tx = tex_axis(__fdiv_rn((float)(x + g.org_x) + 0.5f, fs), w);
+    const int o0 = 3 * tx.i0, o1 = 3 * tx.i1;
+#pragma unroll 2
+    for (int r = 0; r < FBU_ROWS; r++) {
+        const int y = yb + r;
+        if (y >= g.out_h) break;
+        const TexAxis ty = tex_axis(__fdiv_rn((float)(y + g.org_y) + 0.5f, fs), h);
+        const float* r0 = row_ptr(rgb, rgb_pitch, ty.i0);
+        const float* r1 = row_ptr(rgb, rgb_pitch, ty.i1);
+        float* o = row_ptr(out, out_pitch, y) + 3 * x;
 #pragma unroll
-    for (int c = 0; c < 3; c++)
-        o[c] = tex_mix(r0[3 * tx.i0 + c], r0[3 * tx.i1 + c], r1[3 * tx.i0 + c], r1[3 * tx.i1 + c], tx.a, ty.a);
+        for (int c = 0; c < 3; c++)
+            o[c] = tex_mix(__ldg(r0 + o0 + c), __ldg(r0 + o1 + c), __ldg(r1 + o0 + c), __ldg(r1 + o1 + c), tx.a, ty.a);
+    }
 }
 
 // host mirror of gaussin_filter_1D (main.cpp:370-391)
@@ -523,7 +531,7 @@ extern "C" int mfsr_stage_fallback_upsample(const float* rgb, int64_t rgb_pitch,
                                             float* out, int64_t out_pitch, const mfsr_merge_geom* geom, void* stream)
 {
     if (!rgb || !out || !geom || geom->scale < 1) return MFSR_E_INVALID;
-    dim3 b(32, 8), g(cdiv(geom->out_w, 32), cdiv(geom->out_h, 8));
+    dim3 b(32, 8), g(cdiv(geom->out_w, 32), cdiv(geom->out_h, 8 * FBU_ROWS));
     fallback_upsample_kernel<<<g, b, 0, (cudaStream_t)stream>>>(rgb, rgb_pitch, width, height, out, out_pitch, *geom);
     MFSR_LAUNCH_CHECK();
     return MFSR_OK;

@@ -441,7 +441,7 @@ static int run_impl(mfsr_handle h, void* out_any, int64_t out_pitch, int out_on_
                                   h->rgbh_pitch, (const float*)((const char*)cur + h->flow_fs * f + h->flow_pitch * ra), h->flow_pitch,
                                   (float*)((char*)h->mask + h->mask_fs * f + h->mask_pitch * (ra / 2)), h->mask_pitch, (float*)h->mask_tmp, hw2, rh / 2,
                                   p.alpha, p.beta, p.thresholdM, p.mask_erode_radius, st));
-        if (p.mask_erode_radius > 0) h->launches += 2;
+        if (p.mask_erode_radius > 0) h->launches += 1;
     }
     // ---- fallback image (ApplyWeighting's inOutImg): demosaiced reference on the output grid
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_FALLBACK], st));

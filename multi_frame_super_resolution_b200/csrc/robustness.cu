@@ -11,6 +11,11 @@ namespace mfsr {
 
 struct Flow2 { float x, y; };
 
+// MUFU-based square root / reciprocal / exp (<= 2 ulp): the certainty is a tolerance-checked quantity that enters the merge as a
+// smooth weight; the IEEE division / sqrtf / expf sequences were ~250 of the kernel's ~680 instructions per pixel (profiles/r1t).
+__device__ __forceinline__ float rb_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rb_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 // Flow "texture" fetch at half-resolution pixel centre (px, py): normalised coordinate (px + .5) / w on a texture of
 // width 2w lands at texel coordinate 2 px + 1 (+- one ulp of the division, far from any rounding boundary), i.e. exactly
 // between texels 2px and 2px+1 with the 1.8 fixed-point fraction 128/256: the bilinear fetch is tex_mix(..., .5, .5) of the
@@ -68,11 +73,11 @@ robustness_kernel(const float* __restrict__ ref3, const float* __restrict__ mov3
         }
     }
 #pragma unroll
-    for (int c = 0; c < 3; c++) { meanRef[c] /= 9.0f; meanMov[c] /= 9.0f; }
+    for (int c = 0; c < 3; c++) { meanRef[c] *= (1.0f / 9.0f); meanMov[c] *= (1.0f / 9.0f); }
     float meandist = fabsf(meanRef[0] - meanMov[0]) + fabsf(meanRef[1] - meanMov[1]) + fabsf(meanRef[2] - meanMov[2]);
-    meandist /= 3.0f;
+    meandist *= (1.0f / 3.0f);
     maxx *= 0.5f * meandist; maxy *= 0.5f * meandist; minx *= 0.5f * meandist; miny *= 0.5f * meandist;
-    const float Mv = sqrtf((maxx - minx) * (maxx - minx) + (maxy - miny) * (maxy - miny));
+    const float Mv = rb_sqrt((maxx - minx) * (maxx - minx) + (maxy - miny) * (maxy - miny));
     float s = 1.5f;
     if (Mv > thresholdM) s = 0.f;
     const float tt = 0.12f;
@@ -82,39 +87,49 @@ robustness_kernel(const float* __restrict__ ref3, const float* __restrict__ mov3
         float sd = 0.f;
 #pragma unroll
         for (int i = 0; i < 9; i++) sd += (pix[i][c] - meanRef[c]) * (pix[i][c] - meanRef[c]);
-        sd = sqrtf(sd / 9.0f);
-        float sigmaMD = sqrtf(alpha * meanRef[c] + beta);
-        if (c == 1) sigmaMD = sigmaMD / sqrtf(2.0f);          // two greens averaged (:131)
+        sd = rb_sqrt(sd * (1.0f / 9.0f));
+        float sigmaMD = rb_sqrt(alpha * meanRef[c] + beta);
+        if (c == 1) sigmaMD = sigmaMD * 0.70710678118654752440f;          // / sqrt(2): two greens averaged (:131)
         float dist = fabsf(meanRef[c] - meanMov[c]);
         const float sigma = fmaxf(sigmaMD, sd);
-        dist = dist * (sd * sd / (sd * sd + sigmaMD * sigmaMD));
-        mk[c] = fmaxf(fminf(s * expf(-dist * dist / (sigma * sigma)) - tt, 1.0f), 0.0f);
+        dist = dist * (sd * sd * rb_rcp(sd * sd + sigmaMD * sigmaMD));
+        mk[c] = fmaxf(fminf(s * __expf(-dist * dist * rb_rcp(sigma * sigma)) - tt, 1.0f), 0.0f);
     }
     row_ptr(mask, mask_pitch, py)[px] = make_float4(mk[0], mk[1], mk[2], Mv);
 }
 
-// (2r+1)^2 min filter on .xyz, clamp border; .w copied.  Separable: rows then columns.
+// (2r+1)^2 min filter on .xyz, clamp border; .w copied.  One launch: a 32 x 8 output tile with its halo is staged in shared
+// memory, row minima in place, then column minima (the two-launch form moved every mask twice through HBM and was L1-bound:
+// 2r+1 overlapping float4 loads per thread and pass).
+constexpr int ER_MAX = 8, ER_TW = 32, ER_TH = 8;
 __global__ void __launch_bounds__(256)
-erode_rows_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t pitch, int w, int h, int r)
+erode_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t pitch, int w, int h, int r)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-    const float4* row = row_ptr(in, pitch, y);
-    float4 m = row[x];
-    for (int d = -r; d <= r; d++) {
-        const float4 v = row[clampi(x + d, 0, w - 1)];
-        m.x = fminf(m.x, v.x); m.y = fminf(m.y, v.y); m.z = fminf(m.z, v.z);
+    extern __shared__ float4 s_e[];                  // [ER_TH + 2r][ER_TW + 2r] input, then [ER_TH + 2r][ER_TW] row minima
+    const int sw = ER_TW + 2 * r, sh = ER_TH + 2 * r;
+    float4* s_in = s_e;
+    float4* s_row = s_e + sw * sh;
+    const int x0 = blockIdx.x * ER_TW, y0 = blockIdx.y * ER_TH, tid = threadIdx.y * ER_TW + threadIdx.x;
+    for (int i = tid; i < sw * sh; i += ER_TW * ER_TH) {
+        const int ly = i / sw, lx = i - ly * sw;
+        s_in[i] = __ldg(row_ptr(in, pitch, clampi(y0 + ly - r, 0, h - 1)) + clampi(x0 + lx - r, 0, w - 1));
     }
-    row_ptr(out, pitch, y)[x] = m;
-}
-__global__ void __launch_bounds__(256)
-erode_cols_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t pitch, int w, int h, int r)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    __syncthreads();
+    for (int i = tid; i < ER_TW * sh; i += ER_TW * ER_TH) {
+        const int ly = i / ER_TW, lx = i - ly * ER_TW;
+        float4 m = s_in[ly * sw + lx + r];
+        for (int d = 0; d <= 2 * r; d++) {
+            const float4 v = s_in[ly * sw + lx + d];
+            m.x = fminf(m.x, v.x); m.y = fminf(m.y, v.y); m.z = fminf(m.z, v.z);
+        }
+        s_row[i] = m;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if (x >= w || y >= h) return;
-    float4 m = row_ptr(in, pitch, y)[x];
-    for (int d = -r; d <= r; d++) {
-        const float4 v = row_ptr(in, pitch, clampi(y + d, 0, h - 1))[x];
+    float4 m = s_row[(threadIdx.y + r) * ER_TW + threadIdx.x];
+    for (int d = 0; d <= 2 * r; d++) {
+        const float4 v = s_row[(threadIdx.y + d) * ER_TW + threadIdx.x];
         m.x = fminf(m.x, v.x); m.y = fminf(m.y, v.y); m.z = fminf(m.z, v.z);
     }
     row_ptr(out, pitch, y)[x] = m;
@@ -132,13 +147,15 @@ extern "C" int mfsr_stage_robustness(const float* rgb_ref, const float* rgb_mov,
     if (erode_radius > 0 && !scratch) return MFSR_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 b(32, 8), g(cdiv(w, 32), cdiv(h, 8));
+    // with a min filter the raw certainties go to `scratch` and the filter writes `mask`: every mask crosses HBM once per kernel
+    float4* raw_out = erode_radius > 0 ? (float4*)scratch : (float4*)mask;
     robustness_kernel<<<g, b, 0, st>>>(rgb_ref, rgb_mov, rgb_pitch, (const float2*)flow, flow_pitch, 2 * w, 2 * h,
-                                       (float4*)mask, mask_pitch, w, h, alpha, beta, thresholdM);
+                                       raw_out, mask_pitch, w, h, alpha, beta, thresholdM);
     MFSR_LAUNCH_CHECK();
     if (erode_radius > 0) {
-        erode_rows_kernel<<<g, b, 0, st>>>((const float4*)mask, (float4*)scratch, mask_pitch, w, h, erode_radius);
-        MFSR_LAUNCH_CHECK();
-        erode_cols_kernel<<<g, b, 0, st>>>((const float4*)scratch, (float4*)mask, mask_pitch, w, h, erode_radius);
+        const int r = erode_radius;
+        const size_t smem = (size_t)((ER_TW + 2 * r) * (ER_TH + 2 * r) + ER_TW * (ER_TH + 2 * r)) * sizeof(float4);
+        erode_kernel<<<g, b, smem, st>>>((const float4*)scratch, (float4*)mask, mask_pitch, w, h, r);
         MFSR_LAUNCH_CHECK();
     }
     return MFSR_OK;
