@@ -29,7 +29,14 @@ namespace mfsr {
 struct Cfa { int c[4]; };   // c_cfaPattern[2][2] row-major (DeBayerKernels.cu:41), passed by value
 struct F3 { float v[3]; };
 
-__host__ __device__ inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__host__ __device__ inline int clampi(int v, int lo, int hi)
+{
+#ifdef __CUDA_ARCH__
+    return max(lo, min(v, hi));          // two VIMNMX (or one 3-input form) instead of compare + select pairs; lo <= hi everywhere
+#else
+    return v < lo ? lo : (v > hi ? hi : v);
+#endif
+}
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 template <typename T>

@@ -97,7 +97,7 @@ __device__ __forceinline__ bool lk_pinv(float a, float b, float c, float d, floa
 // loop below is a compile-time constant: the first version (runtime hw, per-element clamped stencils, one output per
 // thread in the window sums) executed 1170 instructions per pixel at 82 % issue utilisation (profiles/r1j_lk_ncu.txt).
 //   W region (source + warped): tile + HW + 2 on each side      R region (derivatives): tile + HW
-template <int HW>
+template <int HW, bool BAND>
 __global__ void __launch_bounds__(256, 4)
 lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov, int64_t img_pitch,
                     const float2* __restrict__ flow_in, float2* __restrict__ flow_out, int64_t flow_pitch,
@@ -142,7 +142,7 @@ lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov
                 for (int k = 0; k < CNT; k++) {
                     ly[k] = rg + RG * (k0 + k); ok[k] = ly[k] < WH;
                     gy[k] = clampi(oy + ly[k], 0, h - 1);
-                    if (ok[k]) { srcv[k] = __ldg(ref + (size_t)(gy[k] * pe + gx)); fl[k] = __ldg(flow_in + (size_t)(gy[k] * pf + gx)); }
+                    if (ok[k]) { srcv[k] = __ldg(ref + (unsigned)(gy[k] * pe + gx)); fl[k] = __ldg(flow_in + (unsigned)(gy[k] * pf + gx)); }
                     else { srcv[k] = 0.f; fl[k] = make_float2(0.f, 0.f); }
                 }
                 float t00[CNT], t10[CNT], t01[CNT], t11[CNT], fa[CNT], fb[CNT];
@@ -154,10 +154,12 @@ lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov
                     qy = __fmaf_rn(__fmaf_rn(-fh, qy, py), rh, qy);
                     const TexAxis ax = tex_axis(__fmul_rn(qx, fw), w);
                     TexAxis ay = tex_axis(__fmul_rn(qy, fh), gh);
-                    ay.i0 = clampi(ay.i0 - gy0, 0, h - 1); ay.i1 = clampi(ay.i1 - gy0, 0, h - 1);
-                    const float* r0 = mov + (size_t)(ay.i0 * pe);
-                    const float* r1 = mov + (size_t)(ay.i1 * pe);
-                    if (ok[k]) { t00[k] = __ldg(r0 + ax.i0); t10[k] = __ldg(r0 + ax.i1); t01[k] = __ldg(r1 + ax.i0); t11[k] = __ldg(r1 + ax.i1); }
+                    if (BAND) { ay.i0 = clampi(ay.i0 - gy0, 0, h - 1); ay.i1 = clampi(ay.i1 - gy0, 0, h - 1); }   // whole frame: already in [0, h)
+                    // unsigned 32-bit element indices (the launcher checks pitch * height < 2^31): one IMAD.WIDE per load instead of
+                    // a sign-extended 64-bit add chain (~5 instructions per load)
+                    const unsigned r0 = (unsigned)(ay.i0 * pe), r1 = (unsigned)(ay.i1 * pe);
+                    if (ok[k]) { t00[k] = __ldg(mov + (r0 + (unsigned)ax.i0)); t10[k] = __ldg(mov + (r0 + (unsigned)ax.i1));
+                                 t01[k] = __ldg(mov + (r1 + (unsigned)ax.i0)); t11[k] = __ldg(mov + (r1 + (unsigned)ax.i1)); }
                     else { t00[k] = t10[k] = t01[k] = t11[k] = 0.f; }
                     fa[k] = ax.a; fb[k] = ay.a;
                 }
@@ -247,7 +249,7 @@ lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov
         if (gx < w) {
             float2 fin[4];                     // the four flow values are requested before the first pseudo-inverse
 #pragma unroll
-            for (int p = 0; p < 4; p++) fin[p] = __ldg(flow_in + (size_t)(min(y0 + ly0 + p, h - 1) * pf + gx));
+            for (int p = 0; p < 4; p++) fin[p] = __ldg(flow_in + (unsigned)(min(y0 + ly0 + p, h - 1) * pf + gx));
 #pragma unroll
             for (int p = 0; p < 4; p++) {
                 const int gy = y0 + ly0 + p;
@@ -302,12 +304,16 @@ int mfsr::launch_lk_iteration(const float* ref, const float* mov, int64_t img_pi
     if ((img_pitch & 3) || (flow_pitch & 7) || (int64_t)(img_pitch >> 2) * height >= (1ll << 31) || (int64_t)(flow_pitch >> 3) * height >= (1ll << 31)) return MFSR_E_INVALID;
     if (gh <= 0) { gh = height; gy0 = 0; }
     dim3 b(LTW, 8), g(cdiv(width, LTW), cdiv(height, LTH));
+    const bool band = !(gh == height && gy0 == 0);
+#define MFSR_LK(HW_) do { if (band) lk_iteration_kernel<HW_, true><<<g, b, 0, st>>>(ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0); \
+                          else lk_iteration_kernel<HW_, false><<<g, b, 0, st>>>(ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0); } while (0)
     switch (half_window) {
-        case 1: lk_iteration_kernel<1><<<g, b, 0, st>>>(ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0); break;
-        case 2: lk_iteration_kernel<2><<<g, b, 0, st>>>(ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0); break;
-        case 3: lk_iteration_kernel<3><<<g, b, 0, st>>>(ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0); break;
-        default: lk_iteration_kernel<4><<<g, b, 0, st>>>(ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0); break;
+        case 1: MFSR_LK(1); break;
+        case 2: MFSR_LK(2); break;
+        case 3: MFSR_LK(3); break;
+        default: MFSR_LK(4); break;
     }
+#undef MFSR_LK
     MFSR_LAUNCH_CHECK();
     return MFSR_OK;
 }
