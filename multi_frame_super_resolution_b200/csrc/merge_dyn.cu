@@ -464,45 +464,57 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
     }
     __syncwarp();
 
-    // ---------------- phase 1b: normalised raw windows (de-interleaved by column parity); a thread owns fixed
-    // 4-column chunks (r, c4) of the window and walks the frames, 4 loads in flight
+    // ---------------- phase 1b: normalised raw windows (de-interleaved by column parity).  Thread t owns the 4-column chunk
+    // position t of the window (row r, chunk c4: computed once, 32-bit offsets inside a frame) and walks the frames four at a
+    // time with the loads in flight; the CH - NT positions beyond the block size are flattened over (position, frame) so that
+    // no thread runs a second walk.  (The fully flattened form spent ~25 instructions per sample on index arithmetic.)
     {
         constexpr int CH = C::RHS * (RWS / 4);
-        const int nraw = N * CH;
-        for (int i0 = tid; i0 < nraw; i0 += 4 * C::NT) {
-            uint2 p4[4]; int ph4[4];
+        constexpr int FSTRIDE = C::FRAME_BYTES / 4;                 // floats between the windows of consecutive frames
+        const unsigned rpitch = (unsigned)A.raw_pitch;
+        const float bk0 = F.black_ph[0], bk1 = F.black_ph[1], bk2 = F.black_ph[2], bk3 = F.black_ph[3];
+        const float iv0 = F.inv_ph[0], iv1 = F.inv_ph[1], iv2 = F.inv_ph[2], iv3 = F.inv_ph[3];
+        auto fetch = [&](int f, int r, int c4, uint2& pv, int& odd) {
+            const int2 fi = fbase[f];
+            const int yy = clampi(fi.y + r, 0, g.raw_h - 1), xx = fi.x + 4 * c4;        // xx is a multiple of 4
+            const char* fb = (const char*)A.raw + A.raw_fs * f;
+            odd = yy & 1;
+            if ((unsigned)xx <= (unsigned)(g.raw_w - 4)) pv = __ldg((const uint2*)(fb + ((unsigned)yy * rpitch + 2u * (unsigned)xx)));
+            else {
+                const uint16_t* rrow = (const uint16_t*)(fb + (unsigned)yy * rpitch);
+                unsigned v[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int i = i0 + k * C::NT;
-                if (i < nraw) {
-                    const int f = i / CH, ii = i - f * CH;
-                    const int r = ii / (RWS / 4), c4 = ii - r * (RWS / 4);
-                    const int2 fi = fbase[f];
-                    const int yy = clampi(fi.y + r, 0, g.raw_h - 1), xx = fi.x + 4 * c4;
-                    const uint16_t* rrow = (const uint16_t*)((const char*)A.raw + A.raw_fs * f + A.raw_pitch * yy);
-                    ph4[k] = (yy & 1) * 2;                               // xx is a multiple of 4
-                    if (xx >= 0 && xx + 3 < g.raw_w) p4[k] = __ldg((const uint2*)(rrow + xx));
-                    else {
-                        unsigned v[4];
-#pragma unroll
-                        for (int q = 0; q < 4; q++) v[q] = __ldg(rrow + clampi(xx + q, 0, g.raw_w - 1));
-                        p4[k] = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
-                    }
-                }
+                for (int q = 0; q < 4; q++) v[q] = __ldg(rrow + clampi(xx + q, 0, g.raw_w - 1));
+                pv = make_uint2(v[0] | (v[1] << 16), v[2] | (v[3] << 16));
             }
+        };
+        auto store = [&](float* rs, uint2 pv, int odd) {
+            const float be = odd ? bk2 : bk0, bo = odd ? bk3 : bk1, ie = odd ? iv2 : iv0, io = odd ? iv3 : iv1;
+            *(float2*)rs = make_float2(((float)(pv.x & 0xffffu) - be) * ie, ((float)(pv.y & 0xffffu) - be) * ie);
+            *(float2*)(rs + RHALF) = make_float2(((float)(pv.x >> 16) - bo) * io, ((float)(pv.y >> 16) - bo) * io);
+        };
+        float* win0 = (float*)(smem + C::SHIFT_BYTES);
+        if (tid < CH) {
+            const int r = tid / (RWS / 4), c4 = tid - r * (RWS / 4);
+            float* rs = win0 + r * RWS + 2 * c4;
+            for (int f0 = 0; f0 < N; f0 += 4) {
+                uint2 p4[4]; int o4[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int i = i0 + k * C::NT;
-                if (i < nraw) {
-                    const int f = i / CH, ii = i - f * CH;
-                    const int r = ii / (RWS / 4), c4 = ii - r * (RWS / 4);
-                    const uint2 p = p4[k];
-                    const int ph = ph4[k];
-                    const float be = F.black_ph[ph], bo = F.black_ph[ph + 1], ie = F.inv_ph[ph], io = F.inv_ph[ph + 1];
-                    float* rs = (float*)(smem + (size_t)f * C::FRAME_BYTES + C::SHIFT_BYTES) + r * RWS + 2 * c4;
-                    *(float2*)rs = make_float2(((float)(p.x & 0xffffu) - be) * ie, ((float)(p.y & 0xffffu) - be) * ie);
-                    *(float2*)(rs + RHALF) = make_float2(((float)(p.x >> 16) - bo) * io, ((float)(p.y >> 16) - bo) * io);
-                }
+                for (int k = 0; k < 4; k++)
+                    if (f0 + k < N) fetch(f0 + k, r, c4, p4[k], o4[k]);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (f0 + k < N) store(rs + (f0 + k) * FSTRIDE, p4[k], o4[k]);
+            }
+        }
+        if (CH > C::NT) {
+            constexpr int REST = CH > C::NT ? CH - C::NT : 1;
+            for (int i = tid; i < REST * N; i += C::NT) {
+                const int f = i / REST, pp = C::NT + (i - f * REST);
+                const int r = pp / (RWS / 4), c4 = pp - r * (RWS / 4);
+                uint2 pv; int od;
+                fetch(f, r, c4, pv, od);
+                store(win0 + f * FSTRIDE + r * RWS + 2 * c4, pv, od);
             }
         }
     }
@@ -549,6 +561,7 @@ int launch_merge_s2(const MergeArgs& A, cudaStream_t st)
     if (g.org_x < 0 || g.org_y < 0 || (g.raw_w & 1) || (g.raw_h & 1) || g.raw_w < 8 || g.raw_h < 8) return MFSR_E_INVALID;
     // vector loads of the staging phase
     if (((uintptr_t)A.raw & 7) || (A.raw_pitch & 7) || (A.raw_fs & 7)) return MFSR_E_INVALID;
+    if (A.raw_pitch <= 0 || A.raw_pitch * (int64_t)g.raw_h >= (1ll << 32)) return MFSR_E_INVALID;      // 32-bit offsets inside a frame (staging)
     if (((uintptr_t)A.mask & 15) || (A.mask_pitch & 15) || (A.mask_fs & 15) || ((uintptr_t)A.kern & 15) || (A.kern_pitch & 15)) return MFSR_E_INVALID;
     if (((uintptr_t)A.flow & 7) || (A.flow_pitch & 7) || (A.flow_fs & 7)) return MFSR_E_INVALID;
     FastArgs F;
