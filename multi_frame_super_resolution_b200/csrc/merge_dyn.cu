@@ -333,6 +333,42 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
     const int x0 = (int)blockIdx.x * TW - F.x_off, y0 = (int)blockIdx.y * TH - F.y_off;   // window coords of the tile origin
     const int X0abs = x0 + g.org_x, Y0abs = y0 + g.org_y;                                // multiples of 4
 
+#ifndef MFSR_NO_L2_PREFETCH
+    // L2 prefetch of what phase 1 will stage (certainty rows, kernel-parameter rows, fallback rows and the UNSHIFTED raw window):
+    // the addresses are known now, so their DRAM latency overlaps phase 0 instead of following it.  Rows / columns are clamped
+    // into the images; a line the staging does not need after all is harmless.
+    {
+        auto pf = [](const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
+        const int mw = g.raw_w / 2, mh = g.raw_h / 2;
+        const int mx0 = clampi((X0abs >> 2) - 1, 0, mw - 1), my0 = (Y0abs >> 2) - 1;
+        constexpr int ML = (MWS * 16 + 127) / 128 + 1;                       // 128-byte lines per certainty row of the window
+        for (int i = tid; i < N * C::MHS * ML; i += C::NT) {
+            const int f = i / (C::MHS * ML), j = i - f * (C::MHS * ML), r = j / ML, l = j - r * ML;
+            const int cx = min(mx0 + l * 8, mw - 1);
+            pf((const char*)A.mask + A.mask_fs * f + A.mask_pitch * clampi(my0 + r, 0, mh - 1) + 16 * cx);
+        }
+        const int kx0 = clampi((X0abs >> 1) - 1, 0, g.raw_w - 1), ky0 = (Y0abs >> 1) - 1;
+        constexpr int KL = (C::KWS * 16 + 127) / 128 + 1;
+        for (int i = tid; i < C::KHS * KL; i += C::NT) {
+            const int r = i / KL, l = i - r * KL;
+            pf(row_ptr(A.kern, A.kern_pitch, clampi(ky0 + r, 0, g.raw_h - 1)) + min(kx0 + l * 8, g.raw_w - 1));
+        }
+        constexpr int RL = (TW / 2 + 32) * 2 / 128 + 2;                       // raw window: tile footprint + 16 columns each side
+        const int rx0 = clampi((X0abs >> 1) - 16, 0, g.raw_w - 1), ry0 = (Y0abs >> 1) - 4;
+        for (int i = tid; i < N * (TH / 2 + 8) * RL; i += C::NT) {
+            const int f = i / ((TH / 2 + 8) * RL), j = i - f * ((TH / 2 + 8) * RL), r = j / RL, l = j - r * RL;
+            pf((const char*)A.raw + A.raw_fs * f + A.raw_pitch * clampi(ry0 + r, 0, g.raw_h - 1) + 2 * min(rx0 + l * 64, g.raw_w - 1));
+        }
+        if (A.fallback) {
+            constexpr int FL = TW * 12 / 128 + 1;
+            const int fx0 = clampi(x0, 0, g.out_w - 1);
+            for (int i = tid; i < TH * FL; i += C::NT) {
+                const int r = i / FL, l = i - r * FL;
+                pf(row_ptr(A.fallback, A.fb_pitch, clampi(y0 + r, 0, g.out_h - 1)) + 3 * min(fx0 + l * 10, g.out_w - 1));
+            }
+        }
+    }
+#endif
 
     // ---------------- phase 0: integer HR shifts of every tile pixel and frame -> char2 in shared memory.
     // Work item = (frame, row pair): 8 pixels per lane from a 3 x 4 flow window.  Two items are in flight per warp
