@@ -32,6 +32,20 @@
 #define MFSR_STR(x) #x
 #define MFSR_UNROLL(n) _Pragma(MFSR_STR(unroll n))
 
+#ifdef MFSR_MERGE_TIMING
+// debug builds (tools/merge_phases.py): cycles per phase, summed over the CTAs (thread 0 of every CTA)
+__device__ unsigned long long g_merge_phase_cycles[8];
+extern "C" int mfsr_debug_merge_phase_cycles(unsigned long long* host8, int reset)
+{
+    if (host8 && cudaMemcpyFromSymbol(host8, g_merge_phase_cycles, sizeof(g_merge_phase_cycles)) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[8] = {0}; if (cudaMemcpyToSymbol(g_merge_phase_cycles, z, sizeof(z)) != cudaSuccess) return -1; }
+    return 0;
+}
+#define MFSR_TICK(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_merge_phase_cycles[i], (unsigned long long)(t_ - t_prev_)); t_prev_ = t_; } } while (0)
+#else
+#define MFSR_TICK(i)
+#endif
+
 namespace mfsr {
 
 namespace {
@@ -333,6 +347,9 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
     const int x0 = (int)blockIdx.x * TW - F.x_off, y0 = (int)blockIdx.y * TH - F.y_off;   // window coords of the tile origin
     const int X0abs = x0 + g.org_x, Y0abs = y0 + g.org_y;                                // multiples of 4
 
+#ifdef MFSR_MERGE_TIMING
+    long long t_prev_ = clock64();
+#endif
 #ifndef MFSR_NO_L2_PREFETCH
     // L2 prefetch of what phase 1 will stage (certainty rows, kernel-parameter rows, fallback rows and the UNSHIFTED raw window):
     // the addresses are known now, so their DRAM latency overlaps phase 0 instead of following it.  Rows / columns are clamped
@@ -442,6 +459,7 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
             item = next;
         }
     }
+    MFSR_TICK(0);
     // ---------------- phase 1a: certainty planes and kernel-parameter window (independent of the shifts)
     {
         const int mw = g.raw_w / 2, mh = g.raw_h / 2;
@@ -487,7 +505,9 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
             ks[i] = __ldg(row_ptr(A.kern, A.kern_pitch, clampi(ky0 + r, 0, g.raw_h - 1)) + clampi(kx0 + c, 0, g.raw_w - 1));
         }
     }
+    MFSR_TICK(1);
     __syncthreads();
+    MFSR_TICK(2);
     // staged raw window: the tile's own footprint displaced by the MEAN shift, spare rows/columns split evenly.  Every warp
     // derives the (identical) origins itself — a benign same-value race instead of a second block barrier.
     for (int f = lane; f < N; f += 32) {
@@ -554,7 +574,9 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
             }
         }
     }
+    MFSR_TICK(3);
     __syncthreads();
+    MFSR_TICK(4);
 
     // ---------------- phase 2: warp w owns tile row w (Y % 4 == w % 4 == its scheduler): four passes J = 0..3,
     // each a small loop over the frames (one code variant per warp scheduler at any time)
@@ -564,6 +586,11 @@ merge_s2_dyn_kernel(const __grid_constant__ FastArgs F)
         case 2: run_rows<TH, 2>(F, smem, fbase, norm_s, warp, x0, y0, X0abs, Y0abs); break;
         default: run_rows<TH, 3>(F, smem, fbase, norm_s, warp, x0, y0, X0abs, Y0abs); break;
     }
+    MFSR_TICK(5);
+#ifdef MFSR_MERGE_TIMING
+    __syncthreads();
+    MFSR_TICK(6);
+#endif
 }
 
 template <int TH>
