@@ -172,3 +172,51 @@ def test_output_formats(cuda_device):
     assert lib.mfsr_run_format(sr._h, C.c_void_p(u8.data_ptr()), 256 * 2 * 3, 0, 7, 0) == -1          # unknown format
     assert lib.mfsr_run_format(sr._h, C.c_void_p(u8.data_ptr()), 10, 0, 2, 0) == -1                   # pitch below a row
     sr.close()
+
+
+def test_pipeline_edge_bursts(cuda_device):
+    """Edge cases of the burst path against the oracle: a single frame (no pairs, no flow: the merge of the reference alone),
+    the smallest accepted frame (64 x 64, pyramid cut to the levels that fit), the LAST frame as reference, and a static burst
+    (identical frames: every integer tile shift is exactly zero; the sub-pixel part is findMinimum's parabola through an asymmetric
+    SSD valley, kernel.cu:560-636, so it is small but not zero, and it must equal the oracle's bit for bit)."""
+    p = default_params()
+    # single frame
+    fr, _ = synth_burst(1, 128, 160, seed=9)
+    p1 = default_params(); p1.levels = 2
+    sr, out = _run(p1, fr, cuda_device)
+    exp, _ = O.run_pipeline(u16(fr), p1)
+    assert sr.tile_grid()[2] == 0
+    assert np.array_equal(np.isfinite(out), np.isfinite(exp)) and max_abs(np.nan_to_num(out), np.nan_to_num(exp)) <= 1e-3
+    sr.close()
+    # smallest frame, reference = last frame
+    fr, _ = synth_burst(3, 64, 64, seed=10)
+    p2 = default_params(); p2.levels = 1
+    sr, out = _run(p2, fr, cuda_device, ref_idx=2)
+    exp, it = O.run_pipeline(u16(fr), p2, ref_idx=2, keep=True)
+    for k in range(sr.tile_grid()[2]):
+        assert np.array_equal(sr.tile_argmin(k), it["argmin"][k])
+    bad = np.abs(np.nan_to_num(out) - np.nan_to_num(exp)) > 1e-3
+    assert bad.mean() < 2e-3
+    sr.close()
+    # static burst: identical frames
+    fr, _ = synth_burst(1, 192, 256, seed=11)
+    st = fr.repeat(4, 1, 1).contiguous()
+    p3 = default_params(); p3.levels = 3
+    sr, out = _run(p3, st, cuda_device, ref_idx=1)
+    tx, ty, m = sr.tile_grid()
+    for k in range(m):
+        assert not sr.tile_argmin(k).any(), f"pair {k}: non-zero shift between identical frames"
+    _, it = O.run_pipeline(u16(st), p3, ref_idx=1, keep=True)
+    for f in range(4):
+        ts = sr.tile_shifts(f)
+        assert np.array_equal(ts, it["frame_shift"][f]) and np.abs(ts).max() < 0.5
+    assert np.isfinite(out).all()
+    sr.close()
+    # rejected geometries: odd width, below the minimum size
+    from multi_frame_super_resolution_b200._lib import MfsrError
+    with pytest.raises(MfsrError):
+        BurstSuperResolution(p, 0, 63, 64, 2).workspace_bytes
+    sr = BurstSuperResolution(p, 0, 256, 256, 2)
+    with pytest.raises(MfsrError):
+        sr.set_input(torch.zeros((2, 65, 64), dtype=torch.int16, device=cuda_device))
+    sr.close()
