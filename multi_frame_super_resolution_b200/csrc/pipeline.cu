@@ -404,7 +404,9 @@ static int run_impl(mfsr_handle h, void* out_any, int64_t out_pitch, int out_on_
     int ra = 0, rb = hh;
     if (gh > 0 && p.band_margin > 0) {
         const int keepn = p.band_keep_rows > 0 ? p.band_keep_rows : hh - p.band_keep_row0;
-        ra = (p.band_keep_row0 - p.band_margin) & ~1; if (ra < 0) ra = 0;
+        // ra is a multiple of 32 (the LK tile height): a pixel then sits at the same place inside its CTA's row groups as in the
+        // full-frame run, which keeps the re-associated column sums bit-identical
+        ra = p.band_keep_row0 - p.band_margin; if (ra < 0) ra = 0; ra &= ~31;
         rb = (p.band_keep_row0 + keepn + p.band_margin + 1) & ~1; if (rb > hh) rb = hh;
     }
     const int rh = rb - ra, gy0 = p.band_row0 + ra;
