@@ -65,8 +65,9 @@ def test_pipeline_vs_oracle(cuda_device, full_frame):
     both = np.isfinite(out) & np.isfinite(exp)
     assert np.array_equal(np.isfinite(out), np.isfinite(exp))
     bad = np.abs(np.where(both, out, 0) - np.where(both, exp, 0)) > 1e-3
-    assert bad.mean() < 2e-3, f"{bad.mean():.2e} of samples beyond 1e-3"
-    assert psnr(np.where(both, out, 0), np.where(both, exp, 0)) >= 50.0
+    # measured (tools/parity_margins.py, three seeds): <= 7e-6 of the samples beyond 1e-3, PSNR 90 - 148 dB
+    assert bad.mean() < 1e-4, f"{bad.mean():.2e} of samples beyond 1e-3"
+    assert psnr(np.where(both, out, 0), np.where(both, exp, 0)) >= 60.0            # the north star's bar
     st = sr.stage_ms()
     assert set(st) >= {"frontend", "align", "consolidate", "flow", "kernel_params", "robustness", "fallback", "merge"}
     assert sr.launch_count() > 20
