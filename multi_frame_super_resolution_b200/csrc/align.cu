@@ -420,9 +420,64 @@ upsample_shifts_kernel(const __grid_constant__ UpsampleBatch U)
 // lane r owns row r.  Replaces concatenateShifts/copyShiftMatrix/setPointers/transposeShifts/
 // checkForOutliers/getOptimalShifts/separateShifts + 4 cuBLAS batched calls per sweep.
 
+// AtA of the active measurement rows and its inverse by Gauss-Jordan with partial pivoting (one warp, lane r owns row r).
+// Returns false when a pivot vanishes.  Shared by the per-tile kernel and by the one-warp kernel that inverts the FULL system once
+// per burst: with every pair active the matrix is the same for all tiles, so tiles without outliers (most) only load that inverse.
+__device__ __forceinline__ bool ata_inverse(float* a, float* inv, int n1, int m, unsigned long long active, const PairTable& pt, int lane)
+{
+    // AtA (small exact integers) and identity
+    for (int e = lane; e < n1 * n1; e += 32) {
+        const int i = e / n1, j = e - i * n1, lo = min(i, j), hi = max(i, j);
+        int cnt = 0;
+        for (int k = 0; k < m; k++) cnt += ((active >> k) & 1ull) && pt.from[k] <= lo && hi < pt.to[k];
+        a[e] = (float)cnt; inv[e] = (i == j) ? 1.0f : 0.0f;
+    }
+    __syncwarp();
+    bool singular = false;
+    for (int c = 0; c < n1; c++) {
+        // partial pivot: first row with the largest |a[r][c]|, r >= c
+        int piv = c; float best = fabsf(a[c * n1 + c]);
+        for (int r = c + 1; r < n1; r++) { const float v = fabsf(a[r * n1 + c]); if (v > best) { best = v; piv = r; } }
+        if (best < 1e-6f) { singular = true; break; }
+        if (piv != c) {
+            for (int j = lane; j < n1; j += 32) {
+                float tmp = a[c * n1 + j]; a[c * n1 + j] = a[piv * n1 + j]; a[piv * n1 + j] = tmp;
+                tmp = inv[c * n1 + j]; inv[c * n1 + j] = inv[piv * n1 + j]; inv[piv * n1 + j] = tmp;
+            }
+            __syncwarp();
+        }
+        const float d = 1.0f / a[c * n1 + c];
+        __syncwarp();
+        for (int j = lane; j < n1; j += 32) { a[c * n1 + j] *= d; inv[c * n1 + j] *= d; }
+        __syncwarp();
+        if (lane < n1 && lane != c) {
+            const int r = lane;
+            const float f = a[r * n1 + c];
+            if (f != 0.0f)
+                for (int j = 0; j < n1; j++) { a[r * n1 + j] -= f * a[c * n1 + j]; inv[r * n1 + j] -= f * inv[c * n1 + j]; }
+        }
+        __syncwarp();
+    }
+    return !singular;
+}
+
+__global__ void __launch_bounds__(32)
+consolidate_inverse_kernel(PairTable pt, int m, int imageCount, float* __restrict__ inv0)
+{
+    extern __shared__ float cs0[];
+    const int n1 = imageCount - 1, lane = threadIdx.x;
+    float* a = cs0;
+    float* inv = cs0 + n1 * n1;
+    const unsigned long long active = (m >= 64) ? ~0ull : ((1ull << m) - 1ull);
+    const bool ok = ata_inverse(a, inv, n1, m, active, pt, lane);
+    __syncwarp();
+    for (int e = lane; e < n1 * n1; e += 32) inv0[e] = inv[e];
+    if (lane == 0) inv0[n1 * n1] = ok ? 1.0f : 0.0f;
+}
+
 __global__ void __launch_bounds__(128)
 consolidate_kernel(const float2* __restrict__ measured, int64_t tile_stride, int64_t pair_stride, PairTable pt, int m, int imageCount, int nTiles, int referenceImage,
-                   float2* __restrict__ one_to_one, float2* __restrict__ frame_shift, int* __restrict__ status)
+                   float2* __restrict__ one_to_one, float2* __restrict__ frame_shift, int* __restrict__ status, const float* __restrict__ inv0)
 {
     extern __shared__ float cs[];
     const int n1 = imageCount - 1;
@@ -440,38 +495,13 @@ consolidate_kernel(const float2* __restrict__ measured, int64_t tile_stride, int
     int removed = 0, st = 0;
     __syncwarp();
     for (;;) {
-        // AtA (small exact integers) and identity
-        for (int e = lane; e < n1 * n1; e += 32) {
-            const int i = e / n1, j = e - i * n1, lo = min(i, j), hi = max(i, j);
-            int cnt = 0;
-            for (int k = 0; k < m; k++) cnt += ((active >> k) & 1ull) && pt.from[k] <= lo && hi < pt.to[k];
-            a[e] = (float)cnt; inv[e] = (i == j) ? 1.0f : 0.0f;
-        }
-        __syncwarp();
-        bool singular = false;
-        for (int c = 0; c < n1; c++) {
-            // partial pivot: first row with the largest |a[r][c]|, r >= c
-            int piv = c; float best = fabsf(a[c * n1 + c]);
-            for (int r = c + 1; r < n1; r++) { const float v = fabsf(a[r * n1 + c]); if (v > best) { best = v; piv = r; } }
-            if (best < 1e-6f) { singular = true; break; }
-            if (piv != c) {
-                for (int j = lane; j < n1; j += 32) {
-                    float tmp = a[c * n1 + j]; a[c * n1 + j] = a[piv * n1 + j]; a[piv * n1 + j] = tmp;
-                    tmp = inv[c * n1 + j]; inv[c * n1 + j] = inv[piv * n1 + j]; inv[piv * n1 + j] = tmp;
-                }
-                __syncwarp();
-            }
-            const float d = 1.0f / a[c * n1 + c];
+        bool singular;
+        if (removed == 0 && inv0 && inv0[n1 * n1] != 0.0f) {       // the full system: inverted once per burst
+            for (int e = lane; e < n1 * n1; e += 32) inv[e] = inv0[e];
+            singular = false;
             __syncwarp();
-            for (int j = lane; j < n1; j += 32) { a[c * n1 + j] *= d; inv[c * n1 + j] *= d; }
-            __syncwarp();
-            if (lane < n1 && lane != c) {
-                const int r = lane;
-                const float f = a[r * n1 + c];
-                if (f != 0.0f)
-                    for (int j = 0; j < n1; j++) { a[r * n1 + j] -= f * a[c * n1 + j]; inv[r * n1 + j] -= f * inv[c * n1 + j]; }
-            }
-            __syncwarp();
+        } else {
+            singular = !ata_inverse(a, inv, n1, m, active, pt, lane);
         }
         if (singular) { for (int i = lane; i < 2 * n1; i += 32) x[i] = 0.0f; st = -1; __syncwarp(); break; }
         // Atb (ascending k), x = inv * Atb (ascending j)
@@ -555,13 +585,18 @@ int mfsr::launch_upsample_shifts(const UpsampleBatch& u, cudaStream_t st)
 
 int mfsr::launch_consolidate(const float2* measured, int64_t tile_stride, int64_t pair_stride, const PairTable& pt, int m,
                              int imageCount, int nTiles, int referenceImage, float2* one_to_one, float2* frame_shift,
-                             int* status, cudaStream_t st)
+                             int* status, float* inv0_scratch, cudaStream_t st)
 {
     const int n1 = imageCount - 1, warps = 4;
     const size_t smem = (size_t)warps * (2 * n1 * n1 + 2 * m + 4 * n1) * sizeof(float);
     if (smem > 48 * 1024) return MFSR_E_INVALID;
+    // inv0_scratch (n1 * n1 + 1 floats, may be null): the inverse of the full system, computed once and shared by all tiles
+    if (inv0_scratch) {
+        consolidate_inverse_kernel<<<1, 32, (size_t)2 * n1 * n1 * sizeof(float), st>>>(pt, m, imageCount, inv0_scratch);
+        MFSR_LAUNCH_CHECK();
+    }
     consolidate_kernel<<<cdiv(nTiles, warps), warps * 32, smem, st>>>(measured, tile_stride, pair_stride, pt, m, imageCount, nTiles,
-                                                                    referenceImage, one_to_one, frame_shift, status);
+                                                                    referenceImage, one_to_one, frame_shift, status, inv0_scratch);
     MFSR_LAUNCH_CHECK();
     return MFSR_OK;
 }
@@ -606,5 +641,5 @@ extern "C" int mfsr_stage_consolidate_shifts(const float* measured, const int* p
         pt.from[k] = (int8_t)pair_from[k]; pt.to[k] = (int8_t)pair_to[k];
     }
     return launch_consolidate((const float2*)measured, m, 1, pt, m, imageCount, tilesX * tilesY, referenceImage,
-                              (float2*)one_to_one, (float2*)frame_shift, status, (cudaStream_t)stream);
+                              (float2*)one_to_one, (float2*)frame_shift, status, nullptr, (cudaStream_t)stream);
 }

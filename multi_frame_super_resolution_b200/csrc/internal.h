@@ -32,7 +32,7 @@ int launch_upsample_shifts(const UpsampleBatch& b, cudaStream_t st);
 // measured element (tile t, pair k) at measured[t*tile_stride + k*pair_stride] (in float2 units)
 int launch_consolidate(const float2* measured, int64_t tile_stride, int64_t pair_stride, const PairTable& pt, int m,
                        int imageCount, int nTiles, int referenceImage, float2* one_to_one, float2* frame_shift,
-                       int* status, cudaStream_t st);
+                       int* status, float* inv0_scratch, cudaStream_t st);      // inv0_scratch: (n-1)^2 + 1 floats or null
 
 // CreateFlowFieldFromTiles for a row band: pixel rows and tile rows are mapped through the FULL frame's normalised texture
 // coordinates (global height gh, global tile rows gty; local row 0 is global row gy0, local tile row 0 is global tile row

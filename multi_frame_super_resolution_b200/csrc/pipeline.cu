@@ -48,7 +48,7 @@ struct mfsr_context {
     float* fallback; float* outbuf; int64_t out_pitch_own;
     std::vector<Level> lv;
     PairTable pt; int m;
-    int2* argmin; float2* one_to_one; float2* frame_shift; int* cons_status;
+    int2* argmin; float2* one_to_one; float2* frame_shift; int* cons_status; float* cons_inv0;
     float2* flow_final;   // which of flowA/flowB holds the final flow
     mfsr_merge_geom geom;
 };
@@ -206,6 +206,7 @@ static size_t carve(mfsr_context* c, char* base, int n, int w, int h)
         c->one_to_one = (float2*)take(nt * 8 * (n > 1 ? n - 1 : 1));
         c->frame_shift = (float2*)take(nt * 8 * n);
         c->cons_status = (int*)take(nt * 4);
+        c->cons_inv0 = (float*)take((size_t)(CONS_MAX_N * CONS_MAX_N + 1) * 4);
     }
     return off;
 }
@@ -389,7 +390,7 @@ static int run_impl(mfsr_handle h, void* out_any, int64_t out_pitch, int out_on_
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_CONSOLIDATE], st));
     const int tx = h->lv[0].tx, ty = h->lv[0].ty, nt = tx * ty;
     if (n > 1) {
-        RUN(launch_consolidate(h->lv[0].shift, 1, nt, h->pt, h->m, n, nt, h->ref_idx, h->one_to_one, h->frame_shift, h->cons_status, st));
+        RUN(launch_consolidate(h->lv[0].shift, 1, nt, h->pt, h->m, n, nt, h->ref_idx, h->one_to_one, h->frame_shift, h->cons_status, h->cons_inv0, st));
     } else {
         MFSR_CUDA_TRY(cudaMemsetAsync(h->frame_shift, 0, (size_t)nt * 8, st));
     }
