@@ -260,6 +260,10 @@ __device__ __forceinline__ void cc_group16(const uint32_t* __restrict__ mov, int
 //  * the window energy sum I^2 comes from row sums + a column prefix (exact integers, any order) instead of a second
 //    dp4a per lag and word;
 //  * a lane computes 4 adjacent lags from one set of loaded words.
+// MT: compile-time search radius (0: read it from the batch).  With M known every i / PWA, i / S, it / NG of the staging loops is
+// a multiply-shift instead of a ~20-instruction integer division: the correlation loop was only a third of the 2200 instructions
+// per tile and pair (gpurun_out/r1r_misc.ncu-rep).
+template <int MT>
 __global__ void __launch_bounds__(128)
 tile_align16_kernel(const __grid_constant__ TileAlignArgs AA)
 {
@@ -267,7 +271,7 @@ tile_align16_kernel(const __grid_constant__ TileAlignArgs AA)
     const TileAlignArgs& A = AA;
     const TileAlignBatch& B = A.b;
     constexpr int T = 16, TW = 4;
-    const int M = B.M, P = T + 2 * M, S = 2 * M + 1, nlag = S * S;
+    const int M = MT ? MT : B.M, P = T + 2 * M, S = 2 * M + 1, nlag = S * S;
     const int PWA = (P + 6) / 4 + 1;
     const int per_warp = P * PWA + T * TW + (P + 1) * S + nlag;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -562,7 +566,13 @@ int mfsr::launch_tile_align(const TileAlignBatch& b, cudaStream_t st)
         const int PWA = (P + 6) / 4 + 1;
         const size_t smem16 = (size_t)4 * (P * PWA + 16 * 4 + (P + 1) * S + S * S) * 4;
         if (smem16 <= 48 * 1024) {
-            tile_align16_kernel<<<dim3(cdiv(b.tx * b.ty, 4), b.n_pairs), 128, smem16, st>>>(A);
+            const dim3 g16(cdiv(b.tx * b.ty, 4), b.n_pairs);
+            switch (b.M) {
+                case 2: tile_align16_kernel<2><<<g16, 128, smem16, st>>>(A); break;
+                case 4: tile_align16_kernel<4><<<g16, 128, smem16, st>>>(A); break;
+                case 8: tile_align16_kernel<8><<<g16, 128, smem16, st>>>(A); break;
+                default: tile_align16_kernel<0><<<g16, 128, smem16, st>>>(A); break;
+            }
             MFSR_LAUNCH_CHECK();
             return MFSR_OK;
         }
