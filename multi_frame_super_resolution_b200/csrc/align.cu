@@ -342,7 +342,27 @@ tile_align16_kernel(const __grid_constant__ TileAlignArgs AA)
     unsigned sumT2 = 0;
     for (int i = lane; i < T * TW; i += 32) sumT2 = __dp4a(s_ref[i], s_ref[i], sumT2);
     for (int o = 16; o > 0; o >>= 1) sumT2 += __shfl_xor_sync(0xffffffffu, sumT2, o);
-    // ---- window energies (boxFilterWithBorderX/Y of I^2, kernel.cu:149,:186): row sums, then column prefix
+    // ---- window energies (boxFilterWithBorderX/Y of I^2, kernel.cu:149,:186): row sums, then column prefix.
+    // Compile-time radius with P <= 32: lane y owns row y — the window at lag 0 is four dp4a, every further lag slides it by one
+    // sample (- leaving^2 + entering^2; exact integers, any order), instead of four funnel shifts + four dp4a per (row, lag).
+    if (MT && P <= 32) {
+        if (lane < P) {
+            const uint32_t* mr = s_mov + lane * PWA;
+            uint32_t V[(T + 2 * (MT ? MT : 1)) / 4 + 1];                       // the row's bytes al .. al + P + 3, realigned
+#pragma unroll
+            for (int k = 0; k < (T + 2 * (MT ? MT : 1)) / 4 + 1; k++) V[k] = al ? __funnelshift_r(mr[k], mr[k + 1], 8 * al) : mr[k];
+            unsigned e = 0;
+#pragma unroll
+            for (int xw = 0; xw < TW; xw++) e = __dp4a(V[xw], V[xw], e);
+            s_cp[(lane + 1) * S] = (int)e;
+#pragma unroll
+            for (int lx = 1; lx < 2 * (MT ? MT : 1) + 1; lx++) {
+                const unsigned out = (V[(lx - 1) >> 2] >> (8 * ((lx - 1) & 3))) & 0xffu, in = (V[(lx + 15) >> 2] >> (8 * ((lx + 15) & 3))) & 0xffu;
+                e = e - out * out + in * in;
+                s_cp[(lane + 1) * S + lx] = (int)e;
+            }
+        }
+    } else
     for (int i = lane; i < P * S; i += 32) {
         const int y = i / S, lx = i - y * S;
         const int b = al + lx, wq = b >> 2, sh = (b & 3) * 8;
