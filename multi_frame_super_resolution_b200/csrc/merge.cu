@@ -136,6 +136,7 @@ extern "C" int mfsr_stage_merge(const uint16_t* raw, int64_t raw_pitch, int64_t 
     A.fallback = fallback; A.fb_pitch = fallback_pitch;
     A.out = out; A.out_pitch = out_pitch;
     A.sum_out = sum_out; A.weight_out = weight_out; A.acc_pitch = acc_pitch;
+    A.sum_in = nullptr; A.weight_in = nullptr;
     A.n_frames = n_frames; A.g = *geom;
     for (int i = 0; i < 4; i++) A.cfa.c[i] = cfa[i];
     for (int i = 0; i < 3; i++) { A.white[i] = white[i]; A.black[i] = black[i]; }

@@ -13,6 +13,7 @@ struct MergeArgs {
     const float*    fallback; int64_t fb_pitch;
     float*          out;  int64_t out_pitch;
     float*          sum_out; float* weight_out; int64_t acc_pitch;
+    const float*    sum_in;  const float* weight_in;      // internal (frame-chunked scale-2 merge): partial sums of earlier frames, acc_pitch
     int n_frames;
     mfsr_merge_geom g;
     Cfa cfa;
@@ -36,6 +37,9 @@ __device__ __forceinline__ float finish_px(float v, int flags)
     }
     return v;
 }
+
+// internal flag of the frame-chunked scale-2 merge: write the partial sums only, no image
+#define MFSR_MERGE_PARTIAL_INTERNAL (1 << 16)
 
 // launcher of the scale-2 fast path (merge_fast.cu); returns MFSR_E_INVALID when the configuration is
 // outside what it supports (the caller then runs the generic kernel).

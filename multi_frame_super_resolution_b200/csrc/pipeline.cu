@@ -46,6 +46,7 @@ struct mfsr_context {
     float4* mask; float4* mask_tmp; int64_t mask_pitch, mask_fs;
     float4* kern; int64_t kern_pitch;
     float* fallback; float* outbuf; int64_t out_pitch_own;
+    float* part_sum; float* part_weight;               // partial sums of the frame-chunked merge (bursts of more than 10 frames), else null
     std::vector<Level> lv;
     PairTable pt; int m;
     int2* argmin; float2* one_to_one; float2* frame_shift; int* cons_status; float* cons_inv0;
@@ -182,6 +183,11 @@ static size_t carve(mfsr_context* c, char* base, int n, int w, int h)
     c->out_pitch_own = (int64_t)g.out_w * 12;
     c->fallback = (float*)take((size_t)c->out_pitch_own * (g.out_h + 2));      // + 2: a band's merge window grows by one
     c->outbuf = (float*)take((size_t)c->out_pitch_own * (g.out_h + 2));        //      row at each interior seam
+    c->part_sum = c->part_weight = nullptr;
+    if (n > 10 && p.scale == 2) {                 // more frames than the 16-row merge tile holds at once: merge in chunks of frames (merge_dyn.cu)
+        c->part_sum = (float*)take((size_t)c->out_pitch_own * (g.out_h + 2));
+        c->part_weight = (float*)take((size_t)c->out_pitch_own * (g.out_h + 2));
+    }
     // measured pairs
     int m = 0;
     for (int i = 0; i < n; i++) for (int j = i + 1; j < n && j - i <= p.pair_span; j++) m++;
@@ -467,7 +473,7 @@ static int run_impl(mfsr_handle h, void* out_any, int64_t out_pitch, int out_on_
     const int64_t dst_pitch = staged ? h->out_pitch_own : out_pitch;
     RUN(mfsr_stage_merge(h->rawp, h->rawp_pitch, h->rawp_fs, (const float*)h->mask, h->mask_pitch, h->mask_fs,
                          (const float*)cur, h->flow_pitch, h->flow_fs, (const float*)h->kern, h->kern_pitch,
-                         h->fallback, h->out_pitch_own, dst, dst_pitch, nullptr, nullptr, 0, n, &mg, cfa,
+                         h->fallback, h->out_pitch_own, dst, dst_pitch, h->part_sum, h->part_weight, h->part_sum ? h->out_pitch_own : 0, n, &mg, cfa,
                          p.white_level, p.black_level, p.weight_threshold, p.merge_flags & ~MFSR_MERGE_NO_FALLBACK, st));
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_DOWNLOAD], st));
     if (staged) {

@@ -142,8 +142,15 @@ def test_merge_many_frames_tile_variants(cuda_device, n):
     flow[2, 40:50, :, 1] -= 40.0
     geom = MergeGeom.full_frame(w, h, 2)
     fb = torch.rand((geom.out_h, geom.out_w, 3), generator=g)
+    # with sum / weight images requested the burst is merged in chunks of frames by the 16-row kernel (partial sums in place) ...
     out, s, wt, exp, es, ew = _run_both(raw, mask, flow, kern, fb, geom, cuda_device)
     assert max_abs(out, exp) <= TOL_MAXABS and psnr(out, exp) >= TOL_PSNR
+    assert max_abs(s, es) <= 1e-3 * max(1.0, float(np.abs(es).max())) and max_abs(wt, ew) <= 1e-3 * max(1.0, float(np.abs(ew).max()))
+    # ... without them every frame is resident at once in the 8- / 4-row variants (or the generic kernel runs)
+    dev = cuda_device
+    out2 = stages.merge(raw.to(dev), mask.to(dev), flow.to(dev), kern.to(dev), fb.to(dev), geom, WHITE, BLACK, 0.1).cpu().numpy()
+    assert max_abs(out2, exp) <= TOL_MAXABS and psnr(out2, exp) >= TOL_PSNR
+    assert max_abs(out2, out) <= 1e-5            # same arithmetic, only the association of the frame sums differs
 
 
 def test_merge_window_offsets_and_odd_geometry(cuda_device):

@@ -15,3 +15,17 @@ for (name, n, h, w, scale, ms, fmt) in (('config5 4K x30 3x', 30, 2160, 3840, 3,
     st = sr.stage_ms()
     print(name, {k: round(v, 2) for k, v in st.items()}, 'sum', round(sum(st.values()), 2), 'MP/s', round(ow * oh / 1e6 / (sum(st.values()) / 1e3)), flush=True)
     sr.close(); del fr, out
+# config 4 size on one GPU (48 MP x 15 frames): the frame-chunked merge path
+for (name, n, h, w) in (('config4 48MP x15 2x', 15, 6048, 8064),):
+    p = default_params()
+    sr = BurstSuperResolution(p, device=0, max_width=w, max_height=h, max_frames=n)
+    fr, sh = synth_burst(n, h, w, seed=4321, device=dev)
+    ow, oh = sr.output_size(w, h)
+    out = torch.empty((oh, ow, 3), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        sr.set_input(fr); sr.next_frame(out=out)
+    torch.cuda.synchronize()
+    st = sr.stage_ms()
+    print(name, {k: round(v, 2) for k, v in st.items()}, 'sum', round(sum(st.values()), 2), 'MP/s', round(ow * oh / 1e6 / (sum(st.values()) / 1e3)),
+          'workspace GB', round(sr.workspace_bytes / 1e9, 2), flush=True)
+    sr.close(); del fr, out
