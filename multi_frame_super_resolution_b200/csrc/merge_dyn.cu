@@ -644,13 +644,18 @@ int launch_merge_s2(const MergeArgs& A, cudaStream_t st)
     static const char* thenv = getenv("MFSR_MERGE_TH");
     const int want = thenv ? atoi(thenv) : 0;
     const size_t n = (size_t)A.n_frames, budget1 = 227 * 1024 - 6144;     // dynamic part; launch_th re-checks against the exact limit
-    // More frames than the 16-row tile holds in shared memory (10 at the default geometry): with sum / weight images available
-    // the burst is merged in balanced chunks of frames with the 16-row kernel (the chunk's partial sums are read-modify-written
+    // More frames than the 20- / 16-row tiles hold in shared memory (9 / 10 at the default geometry): with sum / weight images available
+    // the burst is merged in balanced chunks of frames with the 20-row kernel (the chunk's partial sums are read-modify-written
     // by the same thread, the last chunk normalises) — the 8- and 4-row variants that would hold all frames at once cost 1.6x
     // per pixel and frame (10.1 vs 6.4 ms at config 2), the extra 96 B per pixel and chunk boundary is cheap against that.
-    const size_t cap16 = (budget1 - DCfg<16>::KERN_BYTES) / DCfg<16>::FRAME_BYTES;
-    if (!want && n > cap16 && A.sum_out && A.weight_out && A.acc_pitch >= (int64_t)g.out_w * 12) {
-        const int chunks = (int)((n + cap16 - 1) / cap16), per = (int)((n + chunks - 1) / chunks);
+    // Tile height = warps per SM.  20 rows (640 threads x 96 registers, 191 KB at 8 frames) beat 16 rows by 6 % (6.10 vs 6.49 ms,
+    // same box); 24 rows spill (80 registers), 8 rows are 1.6x slower.  16 rows take one more frame (10) than 20 rows (9).
+    auto fits = [&](size_t frame_bytes, size_t kern_bytes) { return n * frame_bytes + kern_bytes <= budget1; };
+    if (!want && fits(DCfg<20>::FRAME_BYTES, DCfg<20>::KERN_BYTES)) { const int rc20 = launch_th<20>(F, st); if (rc20 != MFSR_E_INVALID) return rc20; }
+    if (!want && fits(DCfg<16>::FRAME_BYTES, DCfg<16>::KERN_BYTES)) { const int rc16 = launch_th<16>(F, st); if (rc16 != MFSR_E_INVALID) return rc16; }
+    const size_t cap20 = (budget1 - DCfg<20>::KERN_BYTES) / DCfg<20>::FRAME_BYTES;
+    if (!want && n > cap20 && A.sum_out && A.weight_out && A.acc_pitch >= (int64_t)g.out_w * 12) {
+        const int chunks = (int)((n + cap20 - 1) / cap20), per = (int)((n + chunks - 1) / chunks);
         for (int c = 0, f0 = 0; c < chunks; c++, f0 += per) {
             FastArgs Fc = F;
             Fc.a.raw = (const uint16_t*)((const char*)A.raw + A.raw_fs * f0);
@@ -659,17 +664,18 @@ int launch_merge_s2(const MergeArgs& A, cudaStream_t st)
             Fc.a.n_frames = (int)n - f0 < per ? (int)n - f0 : per;
             Fc.a.sum_in = c ? A.sum_out : nullptr; Fc.a.weight_in = c ? A.weight_out : nullptr;
             if (c < chunks - 1) { Fc.a.flags |= MFSR_MERGE_PARTIAL_INTERNAL; Fc.a.fallback = nullptr; }
-            const int rcc = launch_th<16>(Fc, st);
+            const int rcc = launch_th<20>(Fc, st);
             if (rcc != MFSR_OK) return rcc;
         }
         return MFSR_OK;
     }
     int rc = MFSR_E_INVALID;
-    if (want == 24 && n * DCfg<24>::FRAME_BYTES + DCfg<24>::KERN_BYTES <= budget1) rc = launch_th<24>(F, st);
-    if (rc == MFSR_E_INVALID && want == 8 && n * DCfg<8>::FRAME_BYTES + DCfg<8>::KERN_BYTES <= budget1) rc = launch_th<8>(F, st);
-    if (rc == MFSR_E_INVALID && n * DCfg<16>::FRAME_BYTES + DCfg<16>::KERN_BYTES <= budget1) rc = launch_th<16>(F, st);
-    if (rc == MFSR_E_INVALID && n * DCfg<8>::FRAME_BYTES + DCfg<8>::KERN_BYTES <= budget1) rc = launch_th<8>(F, st);
-    if (rc == MFSR_E_INVALID && n * DCfg<4>::FRAME_BYTES + DCfg<4>::KERN_BYTES <= budget1) rc = launch_th<4>(F, st);
+    if (want == 24 && fits(DCfg<24>::FRAME_BYTES, DCfg<24>::KERN_BYTES)) rc = launch_th<24>(F, st);
+    if (rc == MFSR_E_INVALID && want == 20 && fits(DCfg<20>::FRAME_BYTES, DCfg<20>::KERN_BYTES)) rc = launch_th<20>(F, st);
+    if (rc == MFSR_E_INVALID && want == 8 && fits(DCfg<8>::FRAME_BYTES, DCfg<8>::KERN_BYTES)) rc = launch_th<8>(F, st);
+    if (rc == MFSR_E_INVALID && fits(DCfg<16>::FRAME_BYTES, DCfg<16>::KERN_BYTES)) rc = launch_th<16>(F, st);
+    if (rc == MFSR_E_INVALID && fits(DCfg<8>::FRAME_BYTES, DCfg<8>::KERN_BYTES)) rc = launch_th<8>(F, st);
+    if (rc == MFSR_E_INVALID && fits(DCfg<4>::FRAME_BYTES, DCfg<4>::KERN_BYTES)) rc = launch_th<4>(F, st);
     return rc;
 }
 
