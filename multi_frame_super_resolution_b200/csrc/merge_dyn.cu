@@ -23,6 +23,9 @@
 //    it (alignment outliers) fetches its 3x3 raw samples from global memory instead, same code after.
 // Taps that hit the clamp range (:414-419) and shifts beyond +-127 take the per-pixel generic path of
 // merge_s2_common.cuh.
+// Tile = 128 x TH output pixels, TH warps: 20 rows when all frames fit the 227 KB of shared memory (up to 9 frames), 16 rows for a
+// 10th frame; longer bursts are merged in chunks of frames by the 20-row kernel when sum / weight images are available (the
+// pipeline provides them), else by the 8- / 4-row variants (launch_merge_s2 at the end of this file has the measurements).
 #include "merge_s2_common.cuh"
 
 // frame-loop unroll factor (1: one code variant of ~2.5 KB per warp scheduler; tools/ab_build.sh for A/B builds)
