@@ -186,3 +186,27 @@ def texture_probe(texels, xn):
     out = torch.zeros_like(xn)
     _ck(lib().ref_texture_probe(_p(texels), texels.numel(), _p(xn), _p(out), xn.numel()), "texture_probe")
     return out
+
+
+def last_kernel_ms() -> float:
+    """Device time of the kernels of the last ref_* call (events around the launches, set-up excluded)."""
+    f = lib().ref_last_kernel_ms
+    f.restype = c_f
+    return float(f())
+
+
+def consolidate(measured, pair_from, pair_to, image_count, tx, ty, reference_image):
+    """Reference shift consolidation: copyShiftMatrix / setPointers / transposeShifts / checkForOutliers / getOptimalShifts
+    (ShiftMinimizerKernels.cu) around cuBLAS batched normal equations (the restated host, oracle/ref_driver.cu).
+    measured: float32 [tiles, m, 2] on the device.  Returns (one_to_one [tiles, n-1, 2], frame_shift [n, ty, tx, 2],
+    status [tiles] (reference: -1 when done), removed [tiles] (measurements removed per tile))."""
+    nt, m = measured.shape[:2]
+    assert nt == tx * ty
+    dev = measured.device
+    o2o = torch.zeros((nt, image_count - 1, 2), dtype=torch.float32, device=dev)
+    fs = torch.zeros((image_count, ty, tx, 2), dtype=torch.float32, device=dev)
+    st = torch.zeros((nt,), dtype=torch.int32, device=dev)
+    rm = torch.zeros((nt,), dtype=torch.int32, device=dev)
+    _ck(lib().ref_consolidate(_p(measured.contiguous()), _i(pair_from), _i(pair_to), m, image_count, tx, ty, reference_image,
+                              _p(o2o), _p(fs), _p(st), _p(rm)), "consolidate")
+    return o2o, fs, st, rm

@@ -19,6 +19,8 @@
  */
 #include <cuda_runtime.h>
 #include <cufft.h>
+#include <cublas_v2.h>
+#include <vector>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -35,6 +37,11 @@ extern "C" { __device__ __constant__ BayerColor c_cfaPattern[2][2] = {{Red, Gree
 
 #define RTRY(e) do { cudaError_t _e = (e); if (_e != cudaSuccess) { fprintf(stderr, "ref_driver: %s at %s:%d\n", cudaGetErrorString(_e), __FILE__, __LINE__); return (int)_e; } } while (0)
 #define RSYNC() do { RTRY(cudaGetLastError()); RTRY(cudaDeviceSynchronize()); } while (0)
+
+/* device time of the kernels of the last ref_* call (events around the launches only: texture / buffer set-up excluded) */
+static cudaEvent_t g_e0, g_e1; static bool g_ev = false; static float g_last_ms = -1.0f;
+#define TIC() do { if (!g_ev) { cudaEventCreate(&g_e0); cudaEventCreate(&g_e1); g_ev = true; } cudaEventRecord(g_e0); } while (0)
+#define TOC() do { cudaEventRecord(g_e1); cudaEventSynchronize(g_e1); cudaEventElapsedTime(&g_last_ms, g_e0, g_e1); } while (0)
 
 static inline dim3 grid2(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y, 1); }
 static const dim3 B2(16, 16, 1);
@@ -85,13 +92,14 @@ __global__ void ref_scale(float* v, float f, size_t n) { size_t i = blockIdx.x *
 
 extern "C" {
 
-int ref_version(void) { return 1; }
+int ref_version(void) { return 2; }
+float ref_last_kernel_ms(void) { return g_last_ms; }
 
 int ref_subsample3(const uint16_t* raw, float* rgb3, float maxVal, int dimX, int dimY, const int cfa[4])
 {
     if (set_cfa(cfa)) return -1;
-    deBayersSubSample3<<<grid2(dimX, dimY, B2), B2>>>((unsigned short*)raw, (float3*)rgb3, maxVal, dimX, dimY, dimX * 12);
-    RSYNC(); return 0;
+    TIC(); deBayersSubSample3<<<grid2(dimX, dimY, B2), B2>>>((unsigned short*)raw, (float3*)rgb3, maxVal, dimX, dimY, dimX * 12);
+    TOC(); RSYNC(); return 0;
 }
 
 /* raw_f: float image; rgb3 must be zeroed by the caller (border stays unwritten) */
@@ -99,9 +107,9 @@ int ref_debayer(const float* raw_f, float* rgb3, int w, int h, const int cfa[4],
 {
     if (set_cfa(cfa)) return -1;
     float3 bp = make_float3(black[0], black[1], black[2]), sc = make_float3(scale[0], scale[1], scale[2]);
-    deBayerGreenKernel<<<grid2(w, h, B2), B2>>>(w, h, raw_f, w * 4, (float3*)rgb3, w * 12, bp, sc);
+    TIC(); deBayerGreenKernel<<<grid2(w, h, B2), B2>>>(w, h, raw_f, w * 4, (float3*)rgb3, w * 12, bp, sc);
     deBayerRedBlueKernel<<<grid2(w, h, B2), B2>>>(w, h, raw_f, w * 4, (float3*)rgb3, w * 12, bp, sc);
-    RSYNC(); return 0;
+    TOC(); RSYNC(); return 0;
 }
 
 /* Full tile-matching chain on float images.  pre2: dense float2 [ty][tx] or NULL.
@@ -118,9 +126,9 @@ int ref_tile_align(const float* ref_img, const float* mov_img, int w, int h, con
     if (!pre2) { RTRY(cudaMalloc(&pre, (size_t)nt * 8)); RTRY(cudaMemset(pre, 0, (size_t)nt * 8)); }
     dim3 bt(8, 8, 4), gt((P + 7) / 8, (P + 7) / 8, (nt + 3) / 4);
     float2 bs = make_float2(bsx, bsy);
-    convertToTilesOverlapBorder<<<gt, bt>>>(ref_img, ta, w, h, w * 4, M, T, tx, ty, bs, rot);
+    float ms_total = 0; TIC(); convertToTilesOverlapBorder<<<gt, bt>>>(ref_img, ta, w, h, w * 4, M, T, tx, ty, bs, rot);
     convertToTilesOverlapPreShift<<<gt, bt>>>(mov_img, tb, (const float2*)(pre2 ? pre2 : pre), tx * 8, w, h, w * 4, M, T, tx, ty, bs, rot);
-    RSYNC();
+    TOC(); ms_total += g_last_ms; RSYNC();
     if (use_fft) {
         cufftHandle r2c, c2r; int n[2] = {P, P};
         size_t cplx = (size_t)nt * P * (P / 2 + 1);
@@ -128,26 +136,26 @@ int ref_tile_align(const float* ref_img, const float* mov_img, int w, int h, con
         RTRY(cudaMalloc(&fa, cplx * 8)); RTRY(cudaMalloc(&fb, cplx * 8));
         if (cufftPlanMany(&r2c, 2, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, nt) != CUFFT_SUCCESS) return -2;
         if (cufftPlanMany(&c2r, 2, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2R, nt) != CUFFT_SUCCESS) return -2;
-        if (cufftExecR2C(r2c, ta, (cufftComplex*)fa) != CUFFT_SUCCESS) return -3;
+        TIC(); if (cufftExecR2C(r2c, ta, (cufftComplex*)fa) != CUFFT_SUCCESS) return -3;
         if (cufftExecR2C(r2c, tb, (cufftComplex*)fb) != CUFFT_SUCCESS) return -3;
         conjugateComplexMulKernel<<<(unsigned)((cplx + 255) / 256), 256>>>(fa, fb, (int)cplx);
         if (cufftExecC2R(c2r, (cufftComplex*)fb, cc) != CUFFT_SUCCESS) return -3;
         ref_scale<<<(unsigned)((tile_elems + 255) / 256), 256>>>(cc, 1.0f / (float)(P * P), tile_elems);
-        RSYNC();
+        TOC(); ms_total += g_last_ms; RSYNC();
         cufftDestroy(r2c); cufftDestroy(c2r); cudaFree(fa); cudaFree(fb);
     } else {
         dim3 bc(8, 8, 1), gc((P + 7) / 8, (P + 7) / 8, nt);
-        ref_direct_cc<<<gc, bc>>>(ta, tb, cc, P, nt);
-        RSYNC();
+        TIC(); ref_direct_cc<<<gc, bc>>>(ta, tb, cc, P, nt);
+        TOC(); ms_total += g_last_ms; RSYNC();
     }
-    squaredSum<<<(nt + 127) / 128, 128>>>(ta, sq, M, T, nt);
+    TIC(); squaredSum<<<(nt + 127) / 128, 128>>>(ta, sq, M, T, nt);
     /* blockDim.x = P, one row per block, one tile per z (kernel.cu:145-147) */
     boxFilterWithBorderX<<<dim3(1, P, nt), dim3(P, 1, 1), P * 4>>>(tb, bx, M, T, nt);
     boxFilterWithBorderY<<<dim3(P, 1, nt), dim3(1, P, 1), P * 4>>>(bx, by, M, T, nt);
     dim3 bn(S, S, 1), gn(1, 1, nt);
     normalizedCC<<<gn, bn>>>(cc, sq, by, ssd, M, T, nt);
     findMinimum<<<(nt + 127) / 128, 128>>>(ssd, (float2*)coord2, tx * 8, M, nt, tx, threshold);
-    RSYNC();
+    TOC(); ms_total += g_last_ms; g_last_ms = ms_total; RSYNC();
     cudaFree(ta); cudaFree(tb); cudaFree(cc); cudaFree(bx); cudaFree(by); cudaFree(sq); if (pre) cudaFree(pre);
     return 0;
 }
@@ -161,47 +169,47 @@ int ref_upsample_shifts(const float* in2, float* out2, int oldLevel, int newLeve
 int ref_flow_from_tiles(const float* tile2, int tilesX, int tilesY, int T, float* flow2, int w, int h, float bsx, float bsy, float rot)
 {
     RefTex t; if (make_tex(&t, tile2, tilesX, tilesY, 2)) return -1;
-    CreateFlowFieldFromTiles<<<grid2(w, h, B2), B2>>>((float2*)flow2, t.tex, T, tilesX, tilesY, w, h, w * 8, make_float2(bsx, bsy), rot);
-    RSYNC(); free_tex(&t); return 0;
+    TIC(); CreateFlowFieldFromTiles<<<grid2(w, h, B2), B2>>>((float2*)flow2, t.tex, T, tilesX, tilesY, w, h, w * 8, make_float2(bsx, bsy), rot);
+    TOC(); RSYNC(); free_tex(&t); return 0;
 }
 
 int ref_warp(const float* flow2, const float* img, float* out, int w, int h)
 {
     RefTex tf, ti; if (make_tex(&tf, flow2, w, h, 2) || make_tex(&ti, img, w, h, 1)) return -1;
-    WarpingKernel<<<grid2(w, h, B2), B2>>>(w, h, w * 4, tf.tex, out, ti.tex);
-    RSYNC(); free_tex(&tf); free_tex(&ti); return 0;
+    TIC(); WarpingKernel<<<grid2(w, h, B2), B2>>>(w, h, w * 4, tf.tex, out, ti.tex);
+    TOC(); RSYNC(); free_tex(&tf); free_tex(&ti); return 0;
 }
 
 int ref_derivatives(const float* src, const float* tgt, float* Ix, float* Iy, float* Iz, int w, int h)
 {
     RefTex ts, tt; if (make_tex(&ts, src, w, h, 1) || make_tex(&tt, tgt, w, h, 1)) return -1;
-    ComputeDerivativesKernel<<<grid2(w, h, B2), B2>>>(w, h, w * 4, Ix, Iy, Iz, ts.tex, tt.tex);
-    RSYNC(); free_tex(&ts); free_tex(&tt); return 0;
+    TIC(); ComputeDerivativesKernel<<<grid2(w, h, B2), B2>>>(w, h, w * 4, Ix, Iy, Iz, ts.tex, tt.tex);
+    TOC(); RSYNC(); free_tex(&ts); free_tex(&tt); return 0;
 }
 
 int ref_derivatives2(const float* img, float* Ix, float* Iy, int w, int h)
 {
     RefTex t; if (make_tex(&t, img, w, h, 1)) return -1;
-    ComputeDerivatives2Kernel<<<grid2(w, h, B2), B2>>>(w, h, w * 4, Ix, Iy, t.tex);
-    RSYNC(); free_tex(&t); return 0;
+    TIC(); ComputeDerivatives2Kernel<<<grid2(w, h, B2), B2>>>(w, h, w * 4, Ix, Iy, t.tex);
+    TOC(); RSYNC(); free_tex(&t); return 0;
 }
 
 int ref_lucas_kanade(float* flow2, const float* Ix, const float* Iy, const float* It, int w, int h, int halfWin, float minDet)
 {
-    lucasKanadeOptim<<<grid2(w, h, B2), B2>>>((float2*)flow2, Ix, Iy, It, w * 8, w * 4, w, h, halfWin, minDet);
-    RSYNC(); return 0;
+    TIC(); lucasKanadeOptim<<<grid2(w, h, B2), B2>>>((float2*)flow2, Ix, Iy, It, w * 8, w * 4, w, h, halfWin, minDet);
+    TOC(); RSYNC(); return 0;
 }
 
 int ref_structure_tensor(const float* Ix, const float* Iy, float* t3, int w, int h)
 {
-    ComputeStructureTensor<<<grid2(w, h, B2), B2>>>(Ix, Iy, (float3*)t3, w, h, w * 4, w * 12);
-    RSYNC(); return 0;
+    TIC(); ComputeStructureTensor<<<grid2(w, h, B2), B2>>>(Ix, Iy, (float3*)t3, w, h, w * 4, w * 12);
+    TOC(); RSYNC(); return 0;
 }
 
 int ref_kernel_param(float* k3, int w, int h, float Dth, float Dtr, float kDetail, float kDenoise, float kStretch, float kShrink)
 {
-    ComputeKernelParam<<<grid2(w, h, B2), B2>>>((float3*)k3, w, h, w * 12, Dth, Dtr, kDetail, kDenoise, kStretch, kShrink);
-    RSYNC(); return 0;
+    TIC(); ComputeKernelParam<<<grid2(w, h, B2), B2>>>((float3*)k3, w, h, w * 12, Dth, Dtr, kDetail, kDenoise, kStretch, kShrink);
+    TOC(); RSYNC(); return 0;
 }
 
 /* mask4 zeroed by the caller; flow2 is fw x fh */
@@ -210,8 +218,8 @@ int ref_robustness_mask(const float* ref3, const float* mov3, float* mask4, cons
 {
     RefTex t; if (make_tex(&t, flow2, fw, fh, 2)) return -1;
     size_t smem = (size_t)B2.x * B2.y * 9 * sizeof(float3);
-    ComputeRobustnessMask<<<grid2(w, h, B2), B2, smem>>>((const float3*)ref3, (const float3*)mov3, (float4*)mask4, t.tex, w, h, w * 12, w * 16, alpha, beta, thresholdM);
-    RSYNC(); free_tex(&t); return 0;
+    TIC(); ComputeRobustnessMask<<<grid2(w, h, B2), B2, smem>>>((const float3*)ref3, (const float3*)mov3, (float4*)mask4, t.tex, w, h, w * 12, w * 16, alpha, beta, thresholdM);
+    TOC(); RSYNC(); free_tex(&t); return 0;
 }
 
 /* one frame of accumulateImagesSuperRes (2x, output dims == raw dims); sum3/weight3 RMW */
@@ -220,9 +228,9 @@ int ref_accumulate_superres(const uint16_t* raw, float* sum3, float* weight3, co
 {
     if (set_cfa(cfa)) return -1;
     RefTex tk, ts; if (make_tex(&tk, kernel4, dimX, dimY, 4) || make_tex(&ts, flow2, dimX, dimY, 2)) return -1;
-    accumulateImagesSuperRes<<<grid2(dimX, dimY, B2), B2>>>((unsigned short*)raw, (float3*)sum3, (float3*)weight3, (const float4*)mask4, tk.tex, ts.tex,
+    TIC(); accumulateImagesSuperRes<<<grid2(dimX, dimY, B2), B2>>>((unsigned short*)raw, (float3*)sum3, (float3*)weight3, (const float4*)mask4, tk.tex, ts.tex,
         make_float3(white[0], white[1], white[2]), make_float3(black[0], black[1], black[2]), dimX, dimY, dimX * 12, (dimX / 2) * 16, dimX * 16, dimX * 8);
-    RSYNC(); free_tex(&tk); free_tex(&ts); return 0;
+    TOC(); RSYNC(); free_tex(&tk); free_tex(&ts); return 0;
 }
 
 /* one frame of accumulateImages (1x). kernel3: float3 image with pitch == output pitch (DeBayerKernels.cu:308) */
@@ -273,6 +281,85 @@ int ref_merge_chain_timed(const uint16_t* raw, const float* mask4, const float* 
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     for (int f = 0; f < n_frames; f++) free_tex(&ts[f]);
     delete[] ts; free_tex(&tk);
+    return 0;
+}
+
+/* ---- shift consolidation (ShiftMinimizerKernels.cu) ------------------------------------------------
+ * Upstream's host runs, per sweep, cuBLAS batched AtA -> matinv -> inv*At -> solved*measured -> A*x and then
+ * checkForOutliers (:81) until no tile removes a measurement.  The host is absent from the reference; this is the
+ * restated one, built on the reference's own kernels copyShiftMatrix (:29), setPointers (:51), transposeShifts (:143),
+ * checkForOutliers (:81), getOptimalShifts (:179) and on cuBLAS batched for the linear algebra.
+ *   measured2   : device float2 [nt][m]   (tile-major, as concatenateShifts :223 produces)
+ *   pair_from/to: host int [m]; row k of the design matrix has ones in columns from..to-1
+ *   one_to_one2 : device float2 [nt][n1]      frame_shift2: device float2 [imageCount][ty][tx]
+ *   status      : device int [nt] final reference status (-1 everywhere when converged)
+ *   removed     : device int [nt] number of measurements checkForOutliers removed per tile (host-side count)
+ */
+__global__ void ref_to_transposed(const float2* m2, float* mT, int nt, int m)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= nt * m) return;
+    int t = i / m, k = i - t * m;
+    mT[2 * (size_t)t * m + k] = m2[i].x; mT[2 * (size_t)t * m + k + m] = m2[i].y;
+}
+__global__ void ref_count_removed(const int* status, int* removed, int nt)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < nt && status[i] >= 0) removed[i]++;
+}
+#define BTRY(e) do { cublasStatus_t _s = (e); if (_s != CUBLAS_STATUS_SUCCESS) { fprintf(stderr, "ref_driver: cublas %d at %s:%d\n", (int)_s, __FILE__, __LINE__); return -4; } } while (0)
+
+int ref_consolidate(const float* measured2, const int* pair_from, const int* pair_to, int m, int imageCount,
+                    int tx, int ty, int referenceImage, float* one_to_one2, float* frame_shift2, int* status, int* removed)
+{
+    const int n1 = imageCount - 1, nt = tx * ty;
+    if (n1 < 1 || n1 > 32 || m < 1) return -1;
+    float *A, *Asafe, *Sq, *Inv, *Solved, *measT, *o2oT, *optT; float2 *meas, *o2o;
+    float **pA, **pAsafe, **pSq, **pInv, **pSolved; float2 **pO2o, **pMeas, **pOpt; int* info;
+    RTRY(cudaMalloc(&A, (size_t)nt * n1 * m * 4)); RTRY(cudaMalloc(&Asafe, (size_t)nt * n1 * m * 4));
+    RTRY(cudaMalloc(&Sq, (size_t)nt * n1 * n1 * 4)); RTRY(cudaMalloc(&Inv, (size_t)nt * n1 * n1 * 4));
+    RTRY(cudaMalloc(&Solved, (size_t)nt * n1 * m * 4));
+    RTRY(cudaMalloc(&measT, (size_t)nt * m * 8)); RTRY(cudaMalloc(&meas, (size_t)nt * m * 8));
+    RTRY(cudaMalloc(&o2oT, (size_t)nt * n1 * 8)); RTRY(cudaMalloc(&o2o, (size_t)nt * n1 * 8)); RTRY(cudaMalloc(&optT, (size_t)nt * m * 8));
+    RTRY(cudaMalloc(&pA, nt * sizeof(void*))); RTRY(cudaMalloc(&pAsafe, nt * sizeof(void*))); RTRY(cudaMalloc(&pSq, nt * sizeof(void*)));
+    RTRY(cudaMalloc(&pInv, nt * sizeof(void*))); RTRY(cudaMalloc(&pSolved, nt * sizeof(void*))); RTRY(cudaMalloc(&pO2o, nt * sizeof(void*)));
+    RTRY(cudaMalloc(&pMeas, nt * sizeof(void*))); RTRY(cudaMalloc(&pOpt, nt * sizeof(void*))); RTRY(cudaMalloc(&info, nt * 4));
+    /* design matrix of tile 0 (column-major m x n1, element idx + col*m as :137 addresses it), replicated by copyShiftMatrix */
+    std::vector<float> a0((size_t)m * n1, 0.0f);
+    for (int k = 0; k < m; k++) for (int c = pair_from[k]; c < pair_to[k]; c++) a0[k + (size_t)c * m] = 1.0f;
+    RTRY(cudaMemcpy(A, a0.data(), a0.size() * 4, cudaMemcpyHostToDevice));
+    const int TB = 128, GB = (nt + TB - 1) / TB;
+    copyShiftMatrix<<<GB, TB>>>(A, nt, imageCount, m);
+    setPointers<<<GB, TB>>>(pA, pAsafe, pSq, pInv, pSolved, pO2o, pMeas, pOpt, A, Asafe, Sq, Inv, Solved,
+                            (float2*)o2oT, (float2*)measT, (float2*)optT, nt, imageCount, m);
+    ref_to_transposed<<<(nt * m + 255) / 256, 256>>>((const float2*)measured2, measT, nt, m);
+    dim3 bt(32, 8), gt((nt + 31) / 32, (m + 7) / 8);
+    transposeShifts<<<gt, bt>>>(meas, measT, o2oT, o2o, nt, imageCount, m);      /* measured (float2) from measuredT */
+    RTRY(cudaMemset(status, 0, nt * 4)); RTRY(cudaMemset(removed, 0, nt * 4));
+    RSYNC();
+    cublasHandle_t hb; BTRY(cublasCreate(&hb));
+    BTRY(cublasSetMathMode(hb, CUBLAS_PEDANTIC_MATH));
+    const float one = 1.0f, zero = 0.0f;
+    std::vector<int> hst(nt);
+    for (int sweep = 0; sweep <= m; sweep++) {
+        BTRY(cublasSgemmBatched(hb, CUBLAS_OP_T, CUBLAS_OP_N, n1, n1, m, &one, (const float* const*)pA, m, (const float* const*)pA, m, &zero, pSq, n1, nt));
+        BTRY(cublasSmatinvBatched(hb, n1, (const float* const*)pSq, n1, pInv, n1, info, nt));
+        BTRY(cublasSgemmBatched(hb, CUBLAS_OP_N, CUBLAS_OP_T, n1, m, n1, &one, (const float* const*)pInv, n1, (const float* const*)pA, m, &zero, pSolved, n1, nt));
+        BTRY(cublasSgemmBatched(hb, CUBLAS_OP_N, CUBLAS_OP_N, n1, 2, m, &one, (const float* const*)pSolved, n1, (const float* const*)pMeas, m, &zero, (float**)pO2o, n1, nt));
+        BTRY(cublasSgemmBatched(hb, CUBLAS_OP_N, CUBLAS_OP_N, m, 2, n1, &one, (const float* const*)pA, m, (const float* const*)pO2o, n1, &zero, (float**)pOpt, m, nt));
+        checkForOutliers<<<GB, TB>>>(meas, optT, A, status, info, nt, imageCount, m);
+        ref_count_removed<<<GB, TB>>>(status, removed, nt);
+        RSYNC();
+        RTRY(cudaMemcpy(hst.data(), status, nt * 4, cudaMemcpyDeviceToHost));
+        bool any = false; for (int t = 0; t < nt; t++) any |= hst[t] >= 0;
+        if (!any) break;
+    }
+    cublasDestroy(hb);
+    transposeShifts<<<gt, bt>>>(meas, measT, o2oT, o2o, nt, imageCount, m);      /* oneToOne (float2) from oneToOneT */
+    RTRY(cudaMemcpy(one_to_one2, o2o, (size_t)nt * n1 * 8, cudaMemcpyDeviceToDevice));
+    for (int f = 0; f < imageCount; f++)
+        getOptimalShifts<<<grid2(tx, ty, B2), B2>>>((float2*)frame_shift2 + (size_t)f * nt, o2o, imageCount, tx, ty, tx * 8, referenceImage, f);
+    RSYNC();
+    cudaFree(A); cudaFree(Asafe); cudaFree(Sq); cudaFree(Inv); cudaFree(Solved); cudaFree(measT); cudaFree(meas); cudaFree(o2oT); cudaFree(o2o); cudaFree(optT);
+    cudaFree(pA); cudaFree(pAsafe); cudaFree(pSq); cudaFree(pInv); cudaFree(pSolved); cudaFree(pO2o); cudaFree(pMeas); cudaFree(pOpt); cudaFree(info);
     return 0;
 }
 

@@ -166,3 +166,22 @@ def test_merge_window_offsets_and_odd_geometry(cuda_device):
         fb = torch.rand((oh, ow, 3), generator=g)
         out, s, wt, exp, es, ew = _run_both(raw, mask, flow, kern, fb, geom, cuda_device)
         assert max_abs(out, exp) <= TOL_MAXABS, (ow, oh, ox, oy)
+
+
+@pytest.mark.skipif(not pyref.available(), reason="oracle/_ref/libmfsr_ref.so not built")
+def test_merge_config2_size_vs_reference_kernels(cuda_device):
+    """BASELINE configs[1] size (4032 x 3024 x 8 frames, 2x) through the reference's own accumulateImagesSuperRes x 8 +
+    ApplyWeighting + GammasRGB (reference geometry: central crop, output dims == raw dims, DeBayerKernels.cu:398-423)
+    and through mfsr_stage_merge on the same device buffers."""
+    n, h, w = 8, 3024, 4032
+    dev = cuda_device
+    raw, mask, flow, kern = synth_merge_inputs(n, h, w, seed=4242, device=dev)
+    geom = MergeGeom.reference(w, h)
+    fb = torch.rand((h, w, 3), generator=torch.Generator().manual_seed(7)).to(dev)
+    out = stages.merge(raw, mask, flow, kern, fb, geom, WHITE, BLACK, 0.1, flags=1)
+    ref = pyref.merge_superres(raw, mask, flow, kern, fb, WHITE, BLACK, 0.1, RGGB, gamma=True)
+    d = (out - ref).abs()
+    bad = float((d > TOL_MAXABS).float().mean())
+    mse = float((d.double() ** 2).mean())
+    assert bad < 1e-4, f"{bad:.2e} of samples beyond 1e-3"
+    assert 10.0 * np.log10(1.0 / max(mse, 1e-30)) >= TOL_PSNR

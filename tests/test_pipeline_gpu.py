@@ -221,3 +221,63 @@ def test_pipeline_edge_bursts(cuda_device):
     with pytest.raises(MfsrError):
         sr.set_input(torch.zeros((2, 65, 64), dtype=torch.int16, device=cuda_device))
     sr.close()
+
+
+def _compare_images(out, exp, frac=1e-4, db=60.0):
+    assert np.array_equal(np.isfinite(out), np.isfinite(exp))
+    both = np.isfinite(out) & np.isfinite(exp)
+    a, b = np.where(both, out, 0), np.where(both, exp, 0)
+    bad = np.abs(a - b) > 1e-3
+    assert bad.mean() < frac, f"{bad.mean():.2e} of samples beyond 1e-3"
+    assert psnr(a, b) >= db
+
+
+def test_pipeline_bundled_burst_config1(cuda_device):
+    """BASELINE configs[0]: the reference's own 5-frame burst (tests/golden/bundled_burst_rggb.npz, made from
+    test_opencv/img_00000{0..4}.png by tests/golden/make_bundled_fixture.py) through the CUDA path against the oracle's chain."""
+    from pathlib import Path
+    fr_np = np.load(Path(__file__).resolve().parent / "golden" / "bundled_burst_rggb.npz")["frames"]
+    fr = torch.from_numpy(fr_np.view(np.int16))
+    p = default_params()
+    sr, out = _run(p, fr, cuda_device, ref_idx=0)
+    exp, it = O.run_pipeline(fr_np, p, ref_idx=0, keep=True)
+    for k in range(sr.tile_grid()[2]):
+        assert np.array_equal(sr.tile_argmin(k), it["argmin"][k]), f"pair {k}"
+    for f in range(5):
+        assert np.array_equal(sr.tile_shifts(f), it["frame_shift"][f])
+    _compare_images(out, exp)
+    sr.close()
+
+
+def test_pipeline_config5_shape(cuda_device):
+    """A config-5-shaped pipeline (3x scale, 4 pyramid levels, 16 frames, large motion) on a small image: integer tile
+    shifts and consolidated shifts bit-exact, merged image within the north star's tolerance of the oracle's chain (the
+    3x merge is only definable against the restatement generalised the same way)."""
+    p = default_params()
+    p.scale = 3
+    p.levels = 4
+    fr, sh = synth_burst(16, 320, 384, seed=505, max_shift=12.0)
+    sr, out = _run(p, fr, cuda_device, ref_idx=0)
+    exp, it = O.run_pipeline(u16(fr), p, ref_idx=0, keep=True)
+    assert out.shape == (960, 1152, 3)
+    for k in range(sr.tile_grid()[2]):
+        assert np.array_equal(sr.tile_argmin(k), it["argmin"][k]), f"pair {k}"
+    for f in range(16):
+        assert np.array_equal(sr.tile_shifts(f), it["frame_shift"][f])
+    _compare_images(out, exp)
+    sr.close()
+
+
+def test_pipeline_config2_full_size_vs_oracle(cuda_device):
+    """BASELINE configs[1] at its full size (4032 x 3024 RGGB x 8, 2x, full frame): the whole CUDA chain against the oracle's
+    whole chain (about 20 s of CPU on the box's cores)."""
+    p = default_params()
+    fr, _ = synth_burst(8, 3024, 4032, seed=1234)
+    sr, out = _run(p, fr, cuda_device, ref_idx=0)
+    exp, it = O.run_pipeline(u16(fr), p, ref_idx=0, keep=True)
+    for k in range(sr.tile_grid()[2]):
+        assert np.array_equal(sr.tile_argmin(k), it["argmin"][k]), f"pair {k}"
+    for f in range(8):
+        assert np.array_equal(sr.tile_shifts(f), it["frame_shift"][f])
+    _compare_images(out, exp)
+    sr.close()

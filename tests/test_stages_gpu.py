@@ -194,6 +194,37 @@ def test_consolidate_shifts(cuda_device, n, span):
         assert (est[::3] >= 1).mean() > 0.9
 
 
+@needs_ref
+@pytest.mark.parametrize("n,span,ref_img", [(5, 2, 2), (8, 2, 4), (8, 7, 0), (15, 2, 7), (3, 2, 1)])
+def test_consolidate_vs_reference_kernels(cuda_device, n, span, ref_img):
+    """The reference's own checkForOutliers / transposeShifts / getOptimalShifts (ShiftMinimizerKernels.cu:81,143,179) around
+    cuBLAS batched normal equations (oracle/ref_driver.cu: ref_consolidate) against the one-warp-per-tile kernel: same
+    measurements removed per tile, shifts equal to the round-off of two different fp32 inverses."""
+    rng = np.random.default_rng(1000 + n * 10 + span)
+    pairs = _pairs(n, span)
+    tx, ty = 9, 7
+    nt = tx * ty
+    seq = rng.uniform(-2, 2, size=(nt, n - 1, 2)).astype(np.float32)
+    meas = np.zeros((nt, len(pairs), 2), np.float32)
+    for k, (i, j) in enumerate(pairs):
+        meas[:, k] = seq[:, i:j].sum(axis=1)
+    meas += rng.normal(0, 0.02, size=meas.shape).astype(np.float32)
+    if len(pairs) > n:
+        bad = rng.integers(0, len(pairs), size=(nt, 2))
+        for t in range(0, nt, 3):
+            meas[t, bad[t, 0]] += 7.0
+            if t % 9 == 0 and bad[t, 1] != bad[t, 0]:
+                meas[t, bad[t, 1]] -= 5.0
+    pf, pt = [a for a, _ in pairs], [b for _, b in pairs]
+    d = torch.from_numpy(meas).to(cuda_device)
+    g1, gfs, gst = stages.consolidate_shifts(d, pf, pt, n, tx, ty, ref_img)
+    r1, rfs, rst, rrm = pyref.consolidate(d, pf, pt, n, tx, ty, ref_img)
+    assert int(rst.max()) == -1                                   # the reference loop converged on every tile
+    assert np.array_equal(gst.cpu().numpy(), rrm.cpu().numpy())   # same number of removed measurements per tile
+    assert max_abs(g1.cpu().numpy(), r1.cpu().numpy()) <= 2e-5
+    assert max_abs(gfs.cpu().numpy(), rfs.cpu().numpy()) <= 1e-4
+
+
 def test_flow_from_tiles(cuda_device):
     rng = np.random.default_rng(4)
     tiles = rng.uniform(-3, 3, size=(11, 15, 2)).astype(np.float32)
@@ -293,13 +324,21 @@ def test_robustness_vs_oracle(cuda_device, burst):
 
 
 @needs_ref
-def test_robustness_vs_reference_kernel(cuda_device, burst):
+@pytest.mark.parametrize("varying", [False, True])
+def test_robustness_vs_reference_kernel(cuda_device, burst, varying):
+    """Constant flow and a smoothly varying one (the texture fetch of RobustnessModell.cu:58 lands on the .5 / .5 position of the
+    full-resolution flow, which the 1.8 fixed-point filter represents exactly)."""
     fr, sh = burst
     d0, d1 = fr[0].to(cuda_device), fr[1].to(cuda_device)
     a, b = stages.subsample3(d0, 1023.0, RGGB), stages.subsample3(d1, 1023.0, RGGB)
     h2, w2 = a.shape[:2]
     flow = torch.zeros((2 * h2, 2 * w2, 2), device=cuda_device)
     flow[..., 0], flow[..., 1] = -sh[1, 0].item(), -sh[1, 1].item()
+    if varying:
+        ys, xs = torch.meshgrid(torch.arange(2 * h2, device=cuda_device, dtype=torch.float32),
+                                torch.arange(2 * w2, device=cuda_device, dtype=torch.float32), indexing="ij")
+        flow[..., 0] += 1.7 * torch.sin(xs / 37.0) + 0.6 * torch.cos(ys / 11.0)
+        flow[..., 1] += 2.1 * torch.cos(ys / 29.0) - 0.4 * torch.sin(xs / 13.0)
     got = stages.robustness(a, b, flow, 1e-3, 1e-5, 0.8, 0).cpu().numpy()
     ref = pyref.robustness_mask(a, b, flow, 1e-3, 1e-5, 0.8).cpu().numpy()
     assert max_abs(got, ref) <= 1e-4
