@@ -34,12 +34,19 @@ def make_case(rng, n, span, tx=9, ty=7):
     for k, (i, j) in enumerate(pairs):
         meas[:, k] = seq[:, i:j].sum(axis=1)
     meas += rng.normal(0, 0.02, size=meas.shape).astype(np.float32)
-    if len(pairs) > n:                       # redundancy: one gross outlier in every third tile, two in every ninth
-        bad = rng.integers(0, len(pairs), size=(nt, 2))
+    # Gross outliers only where they are IDENTIFIABLE: an unknown that appears in just two measurements (the first and last
+    # sequential shift when the pair span is 2) gives those two rows residuals of exactly equal magnitude, so which of them
+    # `dist > max` (ShiftMinimizerKernels.cu:118) removes is decided by the round-off of the linear algebra, not by the data.
+    cover = np.zeros(n - 1, int)
+    for (i, j) in pairs:
+        cover[i:j] += 1
+    ok = [k for k, (i, j) in enumerate(pairs) if cover[i:j].min() >= 3]
+    if ok:
+        bad = rng.integers(0, len(ok), size=(nt, 2))
         for t in range(0, nt, 3):
-            meas[t, bad[t, 0]] += 7.0
-            if t % 9 == 0 and bad[t, 1] != bad[t, 0]:
-                meas[t, bad[t, 1]] -= 5.0
+            meas[t, ok[bad[t, 0]]] += 7.0
+            if t % 9 == 0 and bad[t, 1] != bad[t, 0] and len(ok) > 4:
+                meas[t, ok[bad[t, 1]]] -= 5.0
     return pairs, meas
 
 

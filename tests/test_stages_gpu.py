@@ -209,12 +209,18 @@ def test_consolidate_vs_reference_kernels(cuda_device, n, span, ref_img):
     for k, (i, j) in enumerate(pairs):
         meas[:, k] = seq[:, i:j].sum(axis=1)
     meas += rng.normal(0, 0.02, size=meas.shape).astype(np.float32)
-    if len(pairs) > n:
-        bad = rng.integers(0, len(pairs), size=(nt, 2))
+    # outliers only in identifiable rows (every unknown they touch is measured at least three times): with two, the residuals
+    # of the two rows tie exactly and the removed one depends on the round-off of the solver (tests/golden/make_ref_golden_r2.py)
+    cover = np.zeros(n - 1, int)
+    for (i, j) in pairs:
+        cover[i:j] += 1
+    ok = [k for k, (i, j) in enumerate(pairs) if cover[i:j].min() >= 3]
+    if ok:
+        bad = rng.integers(0, len(ok), size=(nt, 2))
         for t in range(0, nt, 3):
-            meas[t, bad[t, 0]] += 7.0
-            if t % 9 == 0 and bad[t, 1] != bad[t, 0]:
-                meas[t, bad[t, 1]] -= 5.0
+            meas[t, ok[bad[t, 0]]] += 7.0
+            if t % 9 == 0 and bad[t, 1] != bad[t, 0] and len(ok) > 4:
+                meas[t, ok[bad[t, 1]]] -= 5.0
     pf, pt = [a for a, _ in pairs], [b for _, b in pairs]
     d = torch.from_numpy(meas).to(cuda_device)
     g1, gfs, gst = stages.consolidate_shifts(d, pf, pt, n, tx, ty, ref_img)
