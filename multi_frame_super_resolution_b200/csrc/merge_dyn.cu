@@ -612,14 +612,19 @@ int launch_th(const FastArgs& F, cudaStream_t st)
     const mfsr_merge_geom& g = F.a.g;
     const size_t smem = (size_t)C::FRAME_BYTES * F.a.n_frames + C::KERN_BYTES;
     // opt-in shared memory: 227 KB per block on sm_100 minus this instantiation's static tables
-    static size_t max_dyn = 0;
-    if (!max_dyn) {
+    // per device: the attribute belongs to the current device's context (a process may hold handles on several GPUs)
+    static size_t max_dyn_dev[64] = {0};
+    int dev = 0;
+    MFSR_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return MFSR_E_INVALID;
+    if (!max_dyn_dev[dev]) {
         cudaFuncAttributes at;
         MFSR_CUDA_TRY(cudaFuncGetAttributes(&at, merge_s2_dyn_kernel<TH>));
         const size_t lim = (size_t)227 * 1024 - at.sharedSizeBytes;
         MFSR_CUDA_TRY(cudaFuncSetAttribute(merge_s2_dyn_kernel<TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
-        max_dyn = lim;
+        max_dyn_dev[dev] = lim;
     }
+    const size_t max_dyn = max_dyn_dev[dev];
     if (smem > max_dyn) return MFSR_E_INVALID;
     dim3 grid(cdiv(g.out_w + F.x_off, TW), cdiv(g.out_h + F.y_off, TH));
     merge_s2_dyn_kernel<TH><<<grid, C::NT, smem, st>>>(F);
@@ -644,6 +649,34 @@ int launch_merge_s2(const MergeArgs& A, cudaStream_t st)
     for (int c = 0; c < 3; c++) F.inv_white[c] = 1.0f / A.white[c];
     for (int q = 0; q < 4; q++) { F.black_ph[q] = A.black[A.cfa.c[q]]; F.inv_ph[q] = F.inv_white[A.cfa.c[q]]; }
     F.x_off = g.org_x & 3; F.y_off = g.org_y & 3;
+    F.ph2c = 0;
+    for (int q = 0; q < 4; q++) {
+        if (A.cfa.c[q] >= 0 && A.cfa.c[q] < 3) F.ph2c |= 1u << (3 * q + A.cfa.c[q]);
+        for (int c = 0; c < 3; c++) F.cfa_sel[q][c] = (A.cfa.c[q] == c || (c == 2 && (A.cfa.c[q] < 0 || A.cfa.c[q] > 2))) ? 1.0f : 0.0f;
+        F.nbi_ph[q] = -F.black_ph[q] * F.inv_ph[q];
+    }
+    // Round 2: the predicate-free slot kernel (merge_pf.cu) takes every burst it can keep resident (10 frames), longer bursts in
+    // balanced chunks of frames when sum / weight images are available; the kernels below remain for bursts without them.
+    static const char* oldenv = getenv("MFSR_MERGE_OLD");
+    if (!(oldenv && atoi(oldenv))) {
+        const int cap = merge_pf_capacity(), n = A.n_frames;
+        if (n <= cap) return launch_merge_pf(F, st);
+        if (A.sum_out && A.weight_out && A.acc_pitch >= (int64_t)g.out_w * 12) {
+            const int chunks = (n + cap - 1) / cap, per = (n + chunks - 1) / chunks;
+            for (int c = 0, f0 = 0; c < chunks; c++, f0 += per) {
+                FastArgs Fc = F;
+                Fc.a.raw = (const uint16_t*)((const char*)A.raw + A.raw_fs * f0);
+                Fc.a.mask = (const float4*)((const char*)A.mask + A.mask_fs * f0);
+                Fc.a.flow = (const float2*)((const char*)A.flow + A.flow_fs * f0);
+                Fc.a.n_frames = n - f0 < per ? n - f0 : per;
+                Fc.a.sum_in = c ? A.sum_out : nullptr; Fc.a.weight_in = c ? A.weight_out : nullptr;
+                if (c < chunks - 1) { Fc.a.flags |= MFSR_MERGE_PARTIAL_INTERNAL; Fc.a.fallback = nullptr; }
+                const int rcc = launch_merge_pf(Fc, st);
+                if (rcc != MFSR_OK) return rcc;
+            }
+            return MFSR_OK;
+        }
+    }
     static const char* thenv = getenv("MFSR_MERGE_TH");
     const int want = thenv ? atoi(thenv) : 0;
     const size_t n = (size_t)A.n_frames, budget1 = 227 * 1024 - 6144;     // dynamic part; launch_th re-checks against the exact limit

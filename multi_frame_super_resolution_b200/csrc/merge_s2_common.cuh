@@ -21,7 +21,14 @@ struct FastArgs {
     float inv_white[3];
     float black_ph[4], inv_ph[4];   // black level / reciprocal white level per CFA phase (y parity * 2 + x parity)
     int x_off, y_off;            // tile grid origin: window x of tile column 0 is -x_off (absolute X multiple of 4)
+    unsigned ph2c;               // bit 3q + c: CFA phase q has colour c (merge_pf.cu epilogue)
+    float cfa_sel[4][3];         // 1 / 0: CFA phase q has colour c (certainty staging of merge_pf.cu)
+    float nbi_ph[4];             // -black * 1/white per CFA phase (raw staging of merge_pf.cu)
 };
+
+// merge_pf.cu: the predicate-free slot kernel (16-row tiles) and the number of frames it keeps resident
+int launch_merge_pf(const FastArgs& F, cudaStream_t st);
+int merge_pf_capacity();
 
 // integer HR shift of absolute HR pixel (X, Y) in frame `flow`: round(2 * tex(flow)) with the 1.8 fixed-point
 // bilinear model of common.cuh (fractions are exactly .25/.75 at scale 2).

@@ -16,3 +16,13 @@ def test_merge_tap_tables(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "bad 0" in out.stdout
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not available")
+def test_merge_slot_fold(tmp_path):
+    """csrc/merge_slots.h (the predicate-free slot fold of merge_pf.cu) against the reference's per-tap index arithmetic."""
+    exe = tmp_path / "merge_slots_check"
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", str(exe), str(ROOT / "tests" / "host" / "merge_slots_check.cpp")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "bad 0" in out.stdout
