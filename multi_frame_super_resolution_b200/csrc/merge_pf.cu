@@ -58,10 +58,11 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr)
 }
 
 // 13 regression weights of absolute HR pixel (X, Y) (:401, :427-430) from the staged kernel-parameter window
-// (float4 [KHS][KWS], origin (kx0, ky0) in raw coordinates, clamp addressing applied while staging).  Out of line and shared
-// by the 16 (J, YM) variants: inlined it would be ~250 once-executed instructions per pass streaming through the
-// instruction caches.  kwin_s is a 32-bit SHARED address (a generic pointer would make the loads generic).
-static __device__ __noinline__ void compute_weights(unsigned kwin_s, int kws, int kx0, int ky0, int X, int Y, float* __restrict__ wl)
+// (float4 [KHS][KWS], origin (kx0, ky0) in raw coordinates, clamp addressing applied while staging).
+// kwin_s is a 32-bit SHARED address.  Inlined ONCE into the pass loop (the pass index J is a run-time loop there): the weights
+// stay in registers (round 2, ncu: the out-of-line version returned them through local memory and every pass paid that
+// round trip while the other three warps of its scheduler were the only cover).
+__device__ __forceinline__ void compute_weights(unsigned kwin_s, int kws, int kx0, int ky0, int X, int Y, float (&wl)[mt::NW])
 {
     const int fx = ((X - 1) >> 1) - kx0, fy = ((Y - 1) >> 1) - ky0;
     const unsigned a00 = kwin_s + (unsigned)(fy * kws + fx) * 16u, a01 = a00 + (unsigned)kws * 16u;
@@ -95,41 +96,31 @@ static __device__ __noinline__ void compute_weights(unsigned kwin_s, int kws, in
     }
 }
 
-// CFA phase -> colour, ApplyWeighting (kernel.cu:426), GammasRGB (:393), one write of one pixel.  Everything arrives BY VALUE:
-// an out-of-line function reaches kernel parameters only through generic loads.  ph2c: per CFA phase q and colour c the float
-// 1 / 0 "phase q has colour c" as bits of a 12-bit mask (bit 3q + c).
-static __device__ __noinline__ void epilogue_px(float* __restrict__ orow, float* so, float* wo, const float* si, const float* wi,
-                                                unsigned ph2c, float threshold, int flags,
-                                                float a0, float a1, float a2, float a3, float b0, float b1, float b2, float b3, float f0, float f1, float f2)
+// relative class sums (cy*2+cx around the window centre) -> absolute CFA phase: absolute = relative ^ (phy, phx)
+__device__ __forceinline__ void route_add(const float (&t)[4], const float (&u)[4], bool phx, bool phy, float (&acc)[4], float (&wacc)[4])
 {
-    const float acc[4] = {a0, a1, a2, a3}, wacc[4] = {b0, b1, b2, b3}, fb3[3] = {f0, f1, f2};
-    float s3[3] = {0.f, 0.f, 0.f}, w3[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int q = 0; q < 4; q++)
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-            if ((ph2c >> (3 * q + c)) & 1u) { s3[c] += acc[q]; w3[c] += wacc[q]; }
-    if (si) {                              // frame-chunked merge: sums of the earlier chunks
-#pragma unroll
-        for (int c = 0; c < 3; c++) { s3[c] = si[c] + s3[c]; w3[c] = wi[c] + w3[c]; }
-    }
-    if (so) {
-        so[0] = s3[0]; so[1] = s3[1]; so[2] = s3[2];
-        wo[0] = w3[0]; wo[1] = w3[1]; wo[2] = w3[2];
-    }
-    if (flags & MFSR_MERGE_PARTIAL_INTERNAL) return;
-#pragma unroll
-    for (int c = 0; c < 3; c++) orow[c] = finish_px(apply_weighting(s3[c], w3[c], fb3[c], threshold), flags);
+    const float t0 = phx ? t[1] : t[0], t1 = phx ? t[0] : t[1], t2 = phx ? t[3] : t[2], t3 = phx ? t[2] : t[3];
+    const float u0 = phx ? u[1] : u[0], u1 = phx ? u[0] : u[1], u2 = phx ? u[3] : u[2], u3 = phx ? u[2] : u[3];
+    acc[0] += phy ? t2 : t0; acc[1] += phy ? t3 : t1; acc[2] += phy ? t0 : t2; acc[3] += phy ? t1 : t3;
+    wacc[0] += phy ? u2 : u0; wacc[1] += phy ? u3 : u1; wacc[2] += phy ? u0 : u2; wacc[3] += phy ? u1 : u3;
+}
+
+template <int J, int YM>
+__device__ __forceinline__ void fold_rt_case(const float (&w)[mt::NW], float fx, float fy, const float (&Q)[2][2][2][2], const float (&R)[3][3], float (&t)[4], float (&u)[4])
+{
+    ms::pixel_fold<J, YM>(w, fx, 1.0f - fx, fy, 1.0f - fy, Q, R, t, u);
 }
 
 // A pixel-frame that phase 0 could not describe: recomputed from global memory.  Alignment outliers (window not staged) whose
-// taps stay inside the clamp range run the slot fold on 3x3 raw samples fetched from global memory; clamped taps and
-// non-finite / outsized shifts run the reference loop (generic_pixel).  ab[0..3] / ab[4..7]: value / weight sums per ABSOLUTE
-// CFA phase.  wl: the pixel's 13 weights (local memory copy).
-static __device__ __noinline__ void special_pixel(const FastArgs& F, int f, int X, int Y, const float* __restrict__ wl, float* __restrict__ ab)
+// taps stay inside the clamp range run the slot fold on 3x3 raw samples and 2x2 certainty cells fetched from global memory;
+// clamped taps and non-finite / outsized shifts run the reference loop (generic_pixel).  ab[0..3] / ab[4..7]: value / weight sums
+// per ABSOLUTE CFA phase.  The weights are recomputed here (rare path) so that the common path never spills them.
+static __device__ __noinline__ void special_pixel(const FastArgs& F, unsigned kwin_s, int kws, int kx0, int ky0, int f, int X, int Y, float* __restrict__ ab)
 {
     const MergeArgs& A = F.a;
     const mfsr_merge_geom& g = A.g;
+    float wl[mt::NW];
+    compute_weights(kwin_s, kws, kx0, ky0, X, Y, wl);
     const int2 s = shift_global(A, f, X, Y);
     const int Xs = X + s.x, Ys = Y + s.y;
     const int lox = 2 * g.clamp_x0 + 2, hix = 2 * g.clamp_x1 - 1, loy = 2 * g.clamp_y0 + 2, hiy = 2 * g.clamp_y1 - 1;
@@ -139,122 +130,171 @@ static __device__ __noinline__ void special_pixel(const FastArgs& F, int f, int 
         return;
     }
     // unclamped: the taps read raw samples (k-1..k+1, ky-1..ky+1) and certainty cells ((X-2)>>2 .. +1, (Y-2)>>2 .. +1)
-    const int k = Xs >> 1, ky = Ys >> 1;
+    const int k = Xs >> 1, ky = Ys >> 1, phx = k & 1, phy = ky & 1;
     const uint16_t* rawf = (const uint16_t*)((const char*)A.raw + A.raw_fs * f);
     const float4* maskf = (const float4*)((const char*)A.mask + A.mask_fs * f);
-    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int py = -2; py <= 2; py++) {
-        const int ry = (Ys + py) >> 1;
-        const uint16_t* rrow = row_ptr(rawf, A.raw_pitch, ry);
-        const float4* mrow = row_ptr(maskf, A.mask_pitch, (Y + py) >> 2);
-        for (int px = -2; px <= 2; px++) {
-            const int rx = (Xs + px) >> 1;
-            const int q = (ry & 1) * 2 + (rx & 1);
-            const int col = A.cfa.c[q];
-            const int apx = (py < 0 || (py == 0 && px < 0)) ? -px : px, apy = (py < 0 || (py == 0 && px < 0)) ? -py : py;
-            const float wt = wl[apy == 0 ? apx : (apy == 1 ? 5 + apx : 10 + apx)];
-            const float4 m = __ldg(mrow + ((X + px) >> 2));
-            float cert = col == 0 ? m.x : (col == 1 ? m.y : m.z);
-            if (!isfinite(cert)) cert = 0.0f;
-            const float rn = ((float)__ldg(rrow + rx) - A.black[col]) * F.inv_white[col];
-            const float tw = wt * cert;
-            a[q] += tw * rn; b[q] += tw;
-        }
-    }
-    (void)k; (void)ky;
+    unsigned rv[3][3];
+    float4 mv[2][2];
 #pragma unroll
-    for (int q = 0; q < 4; q++) { ab[q] = a[q]; ab[4 + q] = b[q]; }
+    for (int r = 0; r < 3; r++) {
+        const uint16_t* rrow = row_ptr(rawf, A.raw_pitch, ky - 1 + r) + (k - 1);
+#pragma unroll
+        for (int c = 0; c < 3; c++) rv[r][c] = __ldg(rrow + c);
+    }
+#pragma unroll
+    for (int mr = 0; mr < 2; mr++) {
+        const float4* mrow = row_ptr(maskf, A.mask_pitch, ((Y - 2) >> 2) + mr) + ((X - 2) >> 2);
+#pragma unroll
+        for (int mc = 0; mc < 2; mc++) mv[mr][mc] = __ldg(mrow + mc);
+    }
+    float R[3][3], Q[2][2][2][2];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const int ph = ((phy ^ ((r + 1) & 1)) * 2) + (phx ^ ((c + 1) & 1));        // CFA phase of sample (k-1+c, ky-1+r)
+            R[r][c] = fmaf((float)rv[r][c], F.inv_ph[ph], F.nbi_ph[ph]);
+        }
+#pragma unroll
+    for (int mr = 0; mr < 2; mr++)
+#pragma unroll
+        for (int mc = 0; mc < 2; mc++) {
+            const float4 m = mv[mr][mc];
+            const float c0 = isfinite(m.x) ? m.x : 0.f, c1 = isfinite(m.y) ? m.y : 0.f, c2 = isfinite(m.z) ? m.z : 0.f;
+#pragma unroll
+            for (int cy = 0; cy < 2; cy++)
+#pragma unroll
+                for (int cx = 0; cx < 2; cx++) {
+                    const int q = (cy ^ phy) * 2 + (cx ^ phx);
+                    Q[mr][mc][cy][cx] = c0 * F.cfa_sel[q][0] + c1 * F.cfa_sel[q][1] + c2 * F.cfa_sel[q][2];
+                }
+        }
+    const float fx = (float)(Xs & 1), fy = (float)(Ys & 1);
+    float t[4], u[4];
+    switch ((Y & 3) * 4 + (X & 3)) {
+#define MFSR_CASE(YMv, Jv) case YMv * 4 + Jv: fold_rt_case<Jv, YMv>(wl, fx, fy, Q, R, t, u); break;
+        MFSR_CASE(0, 0) MFSR_CASE(0, 1) MFSR_CASE(0, 2) MFSR_CASE(0, 3) MFSR_CASE(1, 0) MFSR_CASE(1, 1) MFSR_CASE(1, 2) MFSR_CASE(1, 3)
+        MFSR_CASE(2, 0) MFSR_CASE(2, 1) MFSR_CASE(2, 2) MFSR_CASE(2, 3) MFSR_CASE(3, 0) MFSR_CASE(3, 1) MFSR_CASE(3, 2) default: fold_rt_case<3, 3>(wl, fx, fy, Q, R, t, u); break;
+#undef MFSR_CASE
+    }
+    float a4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
+    route_add(t, u, phx != 0, phy != 0, a4, b4);
+#pragma unroll
+    for (int q = 0; q < 4; q++) { ab[q] = a4[q]; ab[4 + q] = b4[q]; }
 }
 
-// One pass of one warp: tile row `row` (absolute Y % 4 == YM), the 32 pixels X = X0abs + 4*lane + J.
-template <int TH, int YM, int J>
+// The frame loop of one output pixel: J = X % 4 and YM = Y % 4 are compile time (they fix which certainty cell every tap
+// reads and therefore the slot tables); everything frame dependent comes from the 16-bit descriptor.
+template <int TH, int J, int YM>
+__device__ __forceinline__ void frame_loop(const FastArgs& F, int N, const unsigned char* dp, const unsigned char* rp, const unsigned char* mp, unsigned celloff,
+                                           const float (&W)[mt::NW], unsigned kwin_s, int kx0, int ky0, int X, int Y, float (&acc)[4], float (&wacc)[4])
+{
+    using C = PCfg<TH>;
+#pragma unroll 1
+    for (int f = 0; f < N; f++, dp += C::DESC_BYTES, rp += C::RAW_BYTES, mp += MASK_FRAME_BYTES) {
+        const unsigned d = *(const unsigned short*)dp;
+        const unsigned po = d & 0x3FFCu;
+        if (po < SPECIAL) {
+            const float* pe = (const float*)(rp + po);
+            const float* pc = pe + ((d & 0x4000u) ? 1 - RHALF : RHALF);
+            float R[3][3];
+#pragma unroll
+            for (int r = 0; r < 3; r++) { R[r][0] = pe[r * RWS]; R[r][1] = pc[r * RWS]; R[r][2] = pe[r * RWS + 1]; }
+            const unsigned rq0 = ((d >> 3) & 0x1800u) | celloff, rq1 = rq0 ^ 0x1000u;
+            const float2* q0 = (const float2*)(mp + rq0);
+            const float2* q1 = (const float2*)(mp + rq1);
+            float Q[2][2][2][2];
+#pragma unroll
+            for (int mr = 0; mr < 2; mr++)
+#pragma unroll
+                for (int mc = 0; mc < 2; mc++) {
+                    const float2 v0 = q0[mr * MWS + mc], v1 = q1[mr * MWS + mc];
+                    Q[mr][mc][0][0] = v0.x; Q[mr][mc][0][1] = v0.y; Q[mr][mc][1][0] = v1.x; Q[mr][mc][1][1] = v1.y;
+                }
+            const float fx = (d & 1u) ? 1.0f : 0.0f, fy = (d & 2u) ? 1.0f : 0.0f;
+            float t[4], u[4];
+            ms::pixel_fold<J, YM>(W, fx, 1.0f - fx, fy, 1.0f - fy, Q, R, t, u);
+            route_add(t, u, !(d & 0x4000u), (d & 0x8000u) != 0, acc, wacc);      // the window column parity bit is o = !phx
+        } else {
+            float ab[8];
+            special_pixel(F, kwin_s, C::KWS, kx0, ky0, f, X, Y, ab);
+#pragma unroll
+            for (int q = 0; q < 4; q++) { acc[q] += ab[q]; wacc[q] += ab[4 + q]; }
+        }
+    }
+}
+
+// Phase 2 of one warp: tile row `row`, four passes J = 0..3 over the 32 pixels X = X0abs + 4*lane + J.  The per-pixel prologue
+// (weights) and epilogue (CFA phase -> colour, ApplyWeighting kernel.cu:426, GammasRGB :393, one write) exist once; only the
+// frame loop is specialised (16 copies selected by a switch).
+template <int TH>
 __device__ __forceinline__ void run_row(const FastArgs& F, const unsigned char* smem, int row, int x0, int y0, int X0abs, int Y0abs)
 {
     using C = PCfg<TH>;
     const MergeArgs& A = F.a;
     const mfsr_merge_geom& g = A.g;
     const int lane = threadIdx.x & 31;
-    const int y = y0 + row, Y = Y0abs + row;                  // window / absolute row
-    const int x = x0 + 4 * lane + J, X = X0abs + 4 * lane + J;
     const int N = A.n_frames;
-    if (x < 0 || x >= g.out_w || y < 0 || y >= g.out_h) return;
-    const bool pix_on = x >= 1 && x < g.out_w - 1 && y >= 1 && y < g.out_h - 1;      // the reference skips the window border (:391)
-
-    float acc[4] = {0.f, 0.f, 0.f, 0.f}, wacc[4] = {0.f, 0.f, 0.f, 0.f};
-    float fb3[3] = {0.f, 0.f, 0.f};             // ApplyWeighting's inOutImg value, fetched early: its latency hides behind the frame loop
-    if (A.fallback) {
-        const float* p = row_ptr(A.fallback, A.fb_pitch, y) + 3 * x;
-        fb3[0] = __ldg(p); fb3[1] = __ldg(p + 1); fb3[2] = __ldg(p + 2);
-    }
-    if (pix_on) {
-        const unsigned char* descS = smem;
-        const unsigned char* rawS = smem + (size_t)N * C::DESC_BYTES;
-        const unsigned char* maskS = rawS + (size_t)N * C::RAW_BYTES;
-        const unsigned char* kernS = maskS + (size_t)N * MASK_FRAME_BYTES;
-        float wl[mt::NW], W[mt::NW];
-        compute_weights((unsigned)__cvta_generic_to_shared(kernS), C::KWS, (X0abs >> 1) - 1, (Y0abs >> 1) - 1, X, Y, wl);
-#pragma unroll
-        for (int i = 0; i < mt::NW; i++) W[i] = wl[i];
-        // certainty cell of tap -2 (the slot tables count cells from it), as a byte offset inside a plane
-        const int mx0 = (X0abs >> 2) - 1, my0 = (Y0abs >> 2) - 1;
-        const unsigned celloff = (unsigned)(((((Y - 2) >> 2) - my0) * MWS + (((X - 2) >> 2) - mx0)) * 8);
-        const unsigned char* dp = descS + (row * TW + 4 * lane + J) * 2;
-        const unsigned char* rp = rawS;
-        const unsigned char* mp = maskS;
+    const int y = y0 + row, Y = Y0abs + row;                  // window / absolute row
+    if (y < F.in_y0 || y >= F.in_y1) return;                  // outside the window or in the clamp band
+    const unsigned char* descS = smem;
+    const unsigned char* rawS = smem + (size_t)N * C::DESC_BYTES;
+    const unsigned char* maskS = rawS + (size_t)N * C::RAW_BYTES;
+    const unsigned kwin_s = (unsigned)__cvta_generic_to_shared(maskS + (size_t)N * MASK_FRAME_BYTES);
+    const int kx0 = (X0abs >> 1) - 1, ky0 = (Y0abs >> 1) - 1;
+    const int mx0 = (X0abs >> 2) - 1, my0 = (Y0abs >> 2) - 1;
+    const int YM = row & 3;                                   // Y0abs is a multiple of 4
+    const unsigned rowcell = (unsigned)((((Y - 2) >> 2) - my0) * MWS);
+#ifdef MFSR_PF_SKEW
+    // two of the four warps of a scheduler start half a pass late: their prologues / epilogues (latency bound) then meet the other
+    // two warps' frame loops (issue bound) instead of each other
+    if ((row >> 2) & 1) __nanosleep(MFSR_PF_SKEW);
+#endif
 
 #pragma unroll 1
-        for (int f = 0; f < N; f++, dp += C::DESC_BYTES, rp += C::RAW_BYTES, mp += MASK_FRAME_BYTES) {
-            const unsigned d = *(const unsigned short*)dp;
-            const unsigned po = d & 0x3FFCu;
-            if (po < SPECIAL) {
-                const float* pe = (const float*)(rp + po);
-                const float* pc = pe + ((d & 0x4000u) ? 1 - RHALF : RHALF);
-                float R[3][3];
-#pragma unroll
-                for (int r = 0; r < 3; r++) { R[r][0] = pe[r * RWS]; R[r][1] = pc[r * RWS]; R[r][2] = pe[r * RWS + 1]; }
-                const unsigned rq0 = ((d >> 3) & 0x1800u) | celloff, rq1 = rq0 ^ 0x1000u;
-                const float2* q0 = (const float2*)(mp + rq0);
-                const float2* q1 = (const float2*)(mp + rq1);
-                float Q[2][2][2][2];
-#pragma unroll
-                for (int mr = 0; mr < 2; mr++)
-#pragma unroll
-                    for (int mc = 0; mc < 2; mc++) {
-                        const float2 v0 = q0[mr * MWS + mc], v1 = q1[mr * MWS + mc];
-                        Q[mr][mc][0][0] = v0.x; Q[mr][mc][0][1] = v0.y; Q[mr][mc][1][0] = v1.x; Q[mr][mc][1][1] = v1.y;
-                    }
-                const float fx = (d & 1u) ? 1.0f : 0.0f, fy = (d & 2u) ? 1.0f : 0.0f;
-                float t[4], u[4];
-                ms::pixel_fold<J, YM>(W, fx, 1.0f - fx, fy, 1.0f - fy, Q, R, t, u);
-                // route to absolute CFA phase: absolute = relative ^ (phy, phx); the window column parity bit is o = !phx
-                const bool phx = !(d & 0x4000u), phy = (d & 0x8000u) != 0;
-                const float t0 = phx ? t[1] : t[0], t1 = phx ? t[0] : t[1], t2 = phx ? t[3] : t[2], t3 = phx ? t[2] : t[3];
-                const float u0 = phx ? u[1] : u[0], u1 = phx ? u[0] : u[1], u2 = phx ? u[3] : u[2], u3 = phx ? u[2] : u[3];
-                acc[0] += phy ? t2 : t0; acc[1] += phy ? t3 : t1; acc[2] += phy ? t0 : t2; acc[3] += phy ? t1 : t3;
-                wacc[0] += phy ? u2 : u0; wacc[1] += phy ? u3 : u1; wacc[2] += phy ? u0 : u2; wacc[3] += phy ? u1 : u3;
-            } else {
-                float ab[8];
-                special_pixel(F, f, X, Y, wl, ab);
-#pragma unroll
-                for (int q = 0; q < 4; q++) { acc[q] += ab[q]; wacc[q] += ab[4 + q]; }
+    for (int J = 0; J < 4; J++) {
+        const int x = x0 + 4 * lane + J, X = X0abs + 4 * lane + J;
+        if (x < F.in_x0 || x >= F.in_x1) continue;            // outside the window or in the clamp band (merge_band_kernel's pixels)
+        float fb3[3] = {0.f, 0.f, 0.f};         // ApplyWeighting's inOutImg value, fetched early: its latency hides behind the frame loop
+        if (A.fallback) { const float* fbp = row_ptr(A.fallback, A.fb_pitch, y) + 3 * x; fb3[0] = __ldg(fbp); fb3[1] = __ldg(fbp + 1); fb3[2] = __ldg(fbp + 2); }
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, wacc[4] = {0.f, 0.f, 0.f, 0.f};
+        {
+            float W[mt::NW];
+            compute_weights(kwin_s, C::KWS, kx0, ky0, X, Y, W);
+            const unsigned celloff = (rowcell + (unsigned)(((X - 2) >> 2) - mx0)) * 8u;     // certainty cell of tap -2, byte offset inside a plane
+            const unsigned char* dp = descS + (row * TW + 4 * lane + J) * 2;
+            switch (YM * 4 + J) {
+#define MFSR_CASE(YMv, Jv) case YMv * 4 + Jv: frame_loop<TH, Jv, YMv>(F, N, dp, rawS, maskS, celloff, W, kwin_s, kx0, ky0, X, Y, acc, wacc); break;
+                MFSR_CASE(0, 0) MFSR_CASE(0, 1) MFSR_CASE(0, 2) MFSR_CASE(0, 3) MFSR_CASE(1, 0) MFSR_CASE(1, 1) MFSR_CASE(1, 2) MFSR_CASE(1, 3)
+                MFSR_CASE(2, 0) MFSR_CASE(2, 1) MFSR_CASE(2, 2) MFSR_CASE(2, 3) MFSR_CASE(3, 0) MFSR_CASE(3, 1) MFSR_CASE(3, 2)
+                default: frame_loop<TH, 3, 3>(F, N, dp, rawS, maskS, celloff, W, kwin_s, kx0, ky0, X, Y, acc, wacc); break;
+#undef MFSR_CASE
             }
         }
+        // ---- epilogue: CFA phase -> colour by 0 / 1 blends, partial sums of a frame-chunked merge, normalisation, one write
+        float s3[3], w3[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            s3[c] = acc[0] * F.cfa_sel[0][c] + acc[1] * F.cfa_sel[1][c] + acc[2] * F.cfa_sel[2][c] + acc[3] * F.cfa_sel[3][c];
+            w3[c] = wacc[0] * F.cfa_sel[0][c] + wacc[1] * F.cfa_sel[1][c] + wacc[2] * F.cfa_sel[2][c] + wacc[3] * F.cfa_sel[3][c];
+        }
+        // (row pointers are formed here, after the frame loop: held across it they were spilled and reloaded from local memory)
+        if (A.sum_in) {
+            const float* si = row_ptr(A.sum_in, A.acc_pitch, y) + 3 * x; const float* wi = row_ptr(A.weight_in, A.acc_pitch, y) + 3 * x;
+#pragma unroll
+            for (int c = 0; c < 3; c++) { s3[c] = si[c] + s3[c]; w3[c] = wi[c] + w3[c]; }
+        }
+        if (A.sum_out) {
+            float* so = row_ptr(A.sum_out, A.acc_pitch, y) + 3 * x; float* wo = row_ptr(A.weight_out, A.acc_pitch, y) + 3 * x;
+#pragma unroll
+            for (int c = 0; c < 3; c++) { so[c] = s3[c]; wo[c] = w3[c]; }
+        }
+        if (!(A.flags & MFSR_MERGE_PARTIAL_INTERNAL)) {
+            float* orow = row_ptr(A.out, A.out_pitch, y);
+#pragma unroll
+            for (int c = 0; c < 3; c++) orow[3 * x + c] = finish_px(apply_weighting(s3[c], w3[c], fb3[c], A.threshold), A.flags);
+        }
     }
-
-    epilogue_px(row_ptr(A.out, A.out_pitch, y) + 3 * x, A.sum_out ? row_ptr(A.sum_out, A.acc_pitch, y) + 3 * x : nullptr,
-                A.sum_out ? row_ptr(A.weight_out, A.acc_pitch, y) + 3 * x : nullptr,
-                A.sum_in ? row_ptr(A.sum_in, A.acc_pitch, y) + 3 * x : nullptr, A.sum_in ? row_ptr(A.weight_in, A.acc_pitch, y) + 3 * x : nullptr,
-                F.ph2c, A.threshold, A.flags,
-                acc[0], acc[1], acc[2], acc[3], wacc[0], wacc[1], wacc[2], wacc[3], fb3[0], fb3[1], fb3[2]);
-}
-
-template <int TH, int YM>
-__device__ __forceinline__ void run_rows(const FastArgs& F, const unsigned char* smem, int row, int x0, int y0, int X0abs, int Y0abs)
-{
-    run_row<TH, YM, 0>(F, smem, row, x0, y0, X0abs, Y0abs);
-    run_row<TH, YM, 1>(F, smem, row, x0, y0, X0abs, Y0abs);
-    run_row<TH, YM, 2>(F, smem, row, x0, y0, X0abs, Y0abs);
-    run_row<TH, YM, 3>(F, smem, row, x0, y0, X0abs, Y0abs);
 }
 
 // round-half-away-from-zero of |v| as an integer, without F2I (8 cycles per warp on the conversion pipe): two round-toward-zero
@@ -494,9 +534,57 @@ __device__ __forceinline__ void stage_tile(const FastArgs& F, unsigned char* sme
     }
 }
 
+// L2 prefetch of everything the staging phases of tile (x0, y0) will read (certainty rows, kernel-parameter rows, fallback rows, the
+// UNSHIFTED raw window and the flow window): issued while the previous tile of this persistent CTA is in its frame loops, so the
+// staging loads of the next tile meet L2 instead of DRAM.  Rows / columns are clamped into the images; a line too many is harmless.
+template <int TH>
+__device__ __forceinline__ void prefetch_tile(const FastArgs& F, int x0, int y0)
+{
+    using C = PCfg<TH>;
+    const MergeArgs& A = F.a;
+    const mfsr_merge_geom& g = A.g;
+    const int N = A.n_frames, tid = threadIdx.x;
+    const int X0abs = x0 + g.org_x, Y0abs = y0 + g.org_y;
+    auto pf = [](const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
+    const int mw = g.raw_w / 2, mh = g.raw_h / 2;
+    const int mx0 = clampi((X0abs >> 2) - 1, 0, mw - 1), my0 = (Y0abs >> 2) - 1;
+    constexpr int ML = (MWS * 16 + 127) / 128 + 1;
+    for (int i = tid; i < N * C::MHS * ML; i += C::NT) {
+        const int f = i / (C::MHS * ML), j = i - f * (C::MHS * ML), r = j / ML, l = j - r * ML;
+        pf((const char*)A.mask + A.mask_fs * f + A.mask_pitch * clampi(my0 + r, 0, mh - 1) + 16 * min(mx0 + l * 8, mw - 1));
+    }
+    const int kx0 = clampi((X0abs >> 1) - 1, 0, g.raw_w - 1), ky0 = (Y0abs >> 1) - 1;
+    constexpr int KL = (C::KWS * 16 + 127) / 128 + 1;
+    for (int i = tid; i < C::KHS * KL; i += C::NT) {
+        const int r = i / KL, l = i - r * KL;
+        pf(row_ptr(A.kern, A.kern_pitch, clampi(ky0 + r, 0, g.raw_h - 1)) + min(kx0 + l * 8, g.raw_w - 1));
+    }
+    constexpr int FLL = (C::KWS * 8 + 127) / 128 + 1;                        // flow window: same footprint as the kernel-parameter window
+    for (int i = tid; i < N * C::KHS * FLL; i += C::NT) {
+        const int f = i / (C::KHS * FLL), j = i - f * (C::KHS * FLL), r = j / FLL, l = j - r * FLL;
+        pf((const char*)A.flow + A.flow_fs * f + A.flow_pitch * clampi(ky0 + r, 0, g.raw_h - 1) + 8 * min(kx0 + l * 16, g.raw_w - 1));
+    }
+    constexpr int RL = (TW / 2 + 32) * 2 / 128 + 2;
+    const int rx0 = clampi((X0abs >> 1) - 16, 0, g.raw_w - 1), ry0 = (Y0abs >> 1) - 4;
+    for (int i = tid; i < N * (TH / 2 + 8) * RL; i += C::NT) {
+        const int f = i / ((TH / 2 + 8) * RL), j = i - f * ((TH / 2 + 8) * RL), r = j / RL, l = j - r * RL;
+        pf((const char*)A.raw + A.raw_fs * f + A.raw_pitch * clampi(ry0 + r, 0, g.raw_h - 1) + 2 * min(rx0 + l * 64, g.raw_w - 1));
+    }
+    if (A.fallback) {
+        constexpr int FL = TW * 12 / 128 + 1;
+        const int fx0 = clampi(x0, 0, g.out_w - 1);
+        for (int i = tid; i < TH * FL; i += C::NT) {
+            const int r = i / FL, l = i - r * FL;
+            pf(row_ptr(A.fallback, A.fb_pitch, clampi(y0 + r, 0, g.out_h - 1)) + 3 * min(fx0 + l * 10, g.out_w - 1));
+        }
+    }
+}
+
+// Persistent kernel: one CTA per SM walks the tiles (tile index = blockIdx.x + k * gridDim.x, row-major: concurrent CTAs work on
+// neighbouring tiles and share their halo lines in L2).
 template <int TH>
 __global__ void __launch_bounds__(PCfg<TH>::NT, 1)
-merge_pf_kernel(const __grid_constant__ FastArgs F)
+merge_pf_kernel(const __grid_constant__ FastArgs F, int tiles_x, int n_tiles)
 {
     using C = PCfg<TH>;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -506,49 +594,11 @@ merge_pf_kernel(const __grid_constant__ FastArgs F)
     const mfsr_merge_geom& g = A.g;
     const int N = A.n_frames;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = (int)blockIdx.x * TW - F.x_off, y0 = (int)blockIdx.y * TH - F.y_off;   // window coords of the tile origin
-    const int X0abs = x0 + g.org_x, Y0abs = y0 + g.org_y;                                // multiples of 4
-    unsigned char* descS = smem;
-    unsigned char* rawS = smem + (size_t)N * C::DESC_BYTES;
-    unsigned char* maskS = rawS + (size_t)N * C::RAW_BYTES;
-    unsigned char* kernS = maskS + (size_t)N * MASK_FRAME_BYTES;
+    unsigned char* kernS = smem + (size_t)N * (C::DESC_BYTES + C::RAW_BYTES + MASK_FRAME_BYTES);
     unsigned* colT = (unsigned*)(kernS + C::KERN_BYTES);
     unsigned* rowT = colT + C::VN + 1;
 
-    // ---------------- L2 prefetch of what phase 1 will stage (addresses are known now; their DRAM latency overlaps phase 0)
-    {
-        auto pf = [](const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
-        const int mw = g.raw_w / 2, mh = g.raw_h / 2;
-        const int mx0 = clampi((X0abs >> 2) - 1, 0, mw - 1), my0 = (Y0abs >> 2) - 1;
-        constexpr int ML = (MWS * 16 + 127) / 128 + 1;
-        for (int i = tid; i < N * C::MHS * ML; i += C::NT) {
-            const int f = i / (C::MHS * ML), j = i - f * (C::MHS * ML), r = j / ML, l = j - r * ML;
-            const int cx = min(mx0 + l * 8, mw - 1);
-            pf((const char*)A.mask + A.mask_fs * f + A.mask_pitch * clampi(my0 + r, 0, mh - 1) + 16 * cx);
-        }
-        const int kx0 = clampi((X0abs >> 1) - 1, 0, g.raw_w - 1), ky0 = (Y0abs >> 1) - 1;
-        constexpr int KL = (C::KWS * 16 + 127) / 128 + 1;
-        for (int i = tid; i < C::KHS * KL; i += C::NT) {
-            const int r = i / KL, l = i - r * KL;
-            pf(row_ptr(A.kern, A.kern_pitch, clampi(ky0 + r, 0, g.raw_h - 1)) + min(kx0 + l * 8, g.raw_w - 1));
-        }
-        constexpr int RL = (TW / 2 + 32) * 2 / 128 + 2;
-        const int rx0 = clampi((X0abs >> 1) - 16, 0, g.raw_w - 1), ry0 = (Y0abs >> 1) - 4;
-        for (int i = tid; i < N * (TH / 2 + 8) * RL; i += C::NT) {
-            const int f = i / ((TH / 2 + 8) * RL), j = i - f * ((TH / 2 + 8) * RL), r = j / RL, l = j - r * RL;
-            pf((const char*)A.raw + A.raw_fs * f + A.raw_pitch * clampi(ry0 + r, 0, g.raw_h - 1) + 2 * min(rx0 + l * 64, g.raw_w - 1));
-        }
-        if (A.fallback) {
-            constexpr int FL = TW * 12 / 128 + 1;
-            const int fx0 = clampi(x0, 0, g.out_w - 1);
-            for (int i = tid; i < TH * FL; i += C::NT) {
-                const int r = i / FL, l = i - r * FL;
-                pf(row_ptr(A.fallback, A.fb_pitch, clampi(y0 + r, 0, g.out_h - 1)) + 3 * min(fx0 + l * 10, g.out_w - 1));
-            }
-        }
-    }
-
-    // ---------------- lookup tables of phase 0 (same for every frame: indices are relative to the window origin)
+    // ---------------- lookup tables of phase 0 (same for every tile and frame: indices are relative to the window origin)
     for (int i = tid; i <= C::VN + C::UN + 1; i += C::NT) {
         if (i <= C::VN) {
             const int v = i, cc = v >> 1;
@@ -558,54 +608,142 @@ merge_pf_kernel(const __grid_constant__ FastArgs F)
             rowT[u] = (u == C::UN) ? POISON : (unsigned)(r0 * RWS * 4) | ((unsigned)(u & 1) << 1) | ((unsigned)(r0 & 1) << 15);
         }
     }
-    // ---------------- window origins: the tile's own footprint displaced by the mean shift of a 32-point sample per frame
-    // (spare rows / columns split evenly; x a multiple of 4 for the 8-byte raw loads, y ODD so that the row parity of the window
-    // equals the absolute row parity)
-    if (tid == 0) s_border = 0;
-    __syncthreads();
-    for (int f = warp; f < N; f += C::NW_) {
-        const float2* flow = (const float2*)((const char*)A.flow + A.flow_fs * f);
-        const int sxp = clampi((X0abs >> 1) + 4 + 8 * (lane & 7), 0, g.raw_w - 1);
-        const int syp = clampi((Y0abs >> 1) + ((TH / 2) * (2 * (lane >> 3) + 1)) / 8, 0, g.raw_h - 1);
-        const float2 v = __ldg(row_ptr(flow, A.flow_pitch, syp) + sxp);
-        const bool ok = fabsf(v.x) < 1.0e4f && fabsf(v.y) < 1.0e4f;
-        int sx = ok ? __float2int_rn(2.0f * v.x) : 0, sy = ok ? __float2int_rn(2.0f * v.y) : 0, cnt = ok ? 1 : 0;
-        sx = __reduce_add_sync(0xffffffffu, sx); sy = __reduce_add_sync(0xffffffffu, sy); cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if (lane == 0) {
-            cnt = max(cnt, 1);
-            const int mx = (int)floorf((float)sx / (float)cnt + 0.5f), my = (int)floorf((float)sy / (float)cnt + 0.5f);
-            const int2 fb = make_int2((((X0abs + mx - 2) >> 1) - (RWS - (TW / 2 + 3)) / 2) & ~3,
-                                      (((Y0abs + my - 2) >> 1) - (C::RHS - (TH / 2 + 3)) / 2) | 1);
-            fbase[f] = fb;
-            // clamp range (:414-419): the tile is "interior" when neither its own taps nor any staged window can touch it
-            const int lox = 2 * g.clamp_x0 + 2, hix = 2 * g.clamp_x1 - 1, loy = 2 * g.clamp_y0 + 2, hiy = 2 * g.clamp_y1 - 1;
-            const bool inside = X0abs >= lox && X0abs + TW - 1 <= hix && Y0abs >= loy && Y0abs + TH - 1 <= hiy &&
-                                fb.x >= g.clamp_x0 && fb.x + RWS - 1 <= g.clamp_x1 && fb.y >= g.clamp_y0 && fb.y + C::RHS - 1 <= g.clamp_y1;
-            if (!inside) s_border = 1;
+    int tile = blockIdx.x;
+    if (tile < n_tiles) prefetch_tile<TH>(F, (tile % tiles_x) * TW - F.x_off, (tile / tiles_x) * TH - F.y_off);
+
+    for (; tile < n_tiles; tile += gridDim.x) {
+        const int x0 = (tile % tiles_x) * TW - F.x_off, y0 = (tile / tiles_x) * TH - F.y_off;     // window coords of the tile origin
+        const int X0abs = x0 + g.org_x, Y0abs = y0 + g.org_y;                                  // multiples of 4
+        // ---------------- window origins: the tile's own footprint displaced by the mean shift of a 32-point sample per frame
+        // (spare rows / columns split evenly; x a multiple of 4 for the 8-byte raw loads, y ODD so that the row parity of the
+        // window equals the absolute row parity)
+        if (tid == 0) s_border = 0;
+        __syncthreads();                   // also: the previous tile's frame loops are done with the shared-memory windows
+        for (int f = warp; f < N; f += C::NW_) {
+            const float2* flow = (const float2*)((const char*)A.flow + A.flow_fs * f);
+            const int sxp = clampi((X0abs >> 1) + 4 + 8 * (lane & 7), 0, g.raw_w - 1);
+            const int syp = clampi((Y0abs >> 1) + ((TH / 2) * (2 * (lane >> 3) + 1)) / 8, 0, g.raw_h - 1);
+            const float2 v = __ldg(row_ptr(flow, A.flow_pitch, syp) + sxp);
+            const bool ok = fabsf(v.x) < 1.0e4f && fabsf(v.y) < 1.0e4f;
+            int sx = ok ? __float2int_rn(2.0f * v.x) : 0, sy = ok ? __float2int_rn(2.0f * v.y) : 0, cnt = ok ? 1 : 0;
+            sx = __reduce_add_sync(0xffffffffu, sx); sy = __reduce_add_sync(0xffffffffu, sy); cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0) {
+                cnt = max(cnt, 1);
+                const int mx = (int)floorf((float)sx / (float)cnt + 0.5f), my = (int)floorf((float)sy / (float)cnt + 0.5f);
+                const int2 fb = make_int2((((X0abs + mx - 2) >> 1) - (RWS - (TW / 2 + 3)) / 2) & ~3,
+                                          (((Y0abs + my - 2) >> 1) - (C::RHS - (TH / 2 + 3)) / 2) | 1);
+                fbase[f] = fb;
+                // clamp range (:414-419): the tile is "interior" when neither its own taps nor any staged window can touch it
+                const int lox = 2 * g.clamp_x0 + 2, hix = 2 * g.clamp_x1 - 1, loy = 2 * g.clamp_y0 + 2, hiy = 2 * g.clamp_y1 - 1;
+                const bool inside = X0abs >= lox && X0abs + TW - 1 <= hix && Y0abs >= loy && Y0abs + TH - 1 <= hiy &&
+                                    fb.x >= g.clamp_x0 && fb.x + RWS - 1 <= g.clamp_x1 && fb.y >= g.clamp_y0 && fb.y + C::RHS - 1 <= g.clamp_y1 &&
+                                    (X0abs >> 1) - 2 >= 0 && (X0abs >> 1) + TW / 2 + 2 < g.raw_w && (Y0abs >> 1) - 2 >= 0 && (Y0abs >> 1) + TH / 2 + 2 < g.raw_h;
+                if (!inside) s_border = 1;
+            }
+        }
+        __syncthreads();
+        // ---------------- phases 0 and 1 (independent of each other: the window origins are already known): interior tiles run the
+        // variant without clamp handling
+        if (s_border) stage_tile<TH, true>(F, smem, fbase, x0, y0, X0abs, Y0abs);
+        else stage_tile<TH, false>(F, smem, fbase, x0, y0, X0abs, Y0abs);
+        __syncthreads();
+        // ---------------- the next tile's lines on their way to L2 while this one computes
+        {
+            const int nt = tile + gridDim.x;
+            if (nt < n_tiles) prefetch_tile<TH>(F, (nt % tiles_x) * TW - F.x_off, (nt / tiles_x) * TH - F.y_off);
+        }
+        // ---------------- phase 2: warp w owns tile row w: four passes J = 0..3, each a loop over the frames
+        run_row<TH>(F, smem, warp, x0, y0, X0abs, Y0abs);
+    }
+}
+
+// The clamp band: output pixels within BAND HR pixels of the clamp range (:414-419) — where a tap, shifted or not, can be clamped —
+// and the 1-pixel border of the window that the reference skips (:391).  One thread per band pixel runs the reference loop
+// (generic_pixel) for every frame.  In the tile kernel such a pixel would occupy a whole warp for ~1200 instructions per frame
+// (round 2, ncu: 1.6 % of the warp iterations cost 10 % of the kernel's time); here 32 of them share a warp.
+constexpr int BAND = 8;
+__global__ void __launch_bounds__(128)
+merge_band_kernel(const __grid_constant__ FastArgs F, int n_top, int n_mid_rows, int n_left, int n_right, int total)
+{
+    const MergeArgs& A = F.a;
+    const mfsr_merge_geom& g = A.g;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    // strips: rows [0, in_y0) and [in_y1, out_h) over the full width, then the left / right parts of the rows in between
+    int x, y;
+    const int n_bot_start = n_top * g.out_w, n_bot = (g.out_h - F.in_y1) * g.out_w;
+    if (i < n_bot_start) { y = i / g.out_w; x = i - y * g.out_w; }
+    else if (i < n_bot_start + n_bot) { const int j = i - n_bot_start; y = j / g.out_w; x = j - y * g.out_w; y += F.in_y1; }
+    else {
+        const int j = i - n_bot_start - n_bot, per = n_left + n_right;
+        y = j / per; x = j - y * per; y += F.in_y0;
+        if (x >= n_left) x = F.in_x1 + (x - n_left);
+    }
+    (void)n_mid_rows;
+    const int X = x + g.org_x, Y = y + g.org_y;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, wacc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (x >= 1 && x < g.out_w - 1 && y >= 1 && y < g.out_h - 1) {
+        // 13 weights from global memory (texture model of :401, clamp addressing)
+        float wl[mt::NW];
+        {
+            const int fx = (X - 1) >> 1, fy = (Y - 1) >> 1;
+            const int xa = clampi(fx, 0, g.raw_w - 1), xb = clampi(fx + 1, 0, g.raw_w - 1), ya = clampi(fy, 0, g.raw_h - 1), yb = clampi(fy + 1, 0, g.raw_h - 1);
+            const float4 K00 = __ldg(row_ptr(A.kern, A.kern_pitch, ya) + xa), K10 = __ldg(row_ptr(A.kern, A.kern_pitch, ya) + xb);
+            const float4 K01 = __ldg(row_ptr(A.kern, A.kern_pitch, yb) + xa), K11 = __ldg(row_ptr(A.kern, A.kern_pitch, yb) + xb);
+            const float ta = (X & 1) ? 0.25f : 0.75f, tb = (Y & 1) ? 0.25f : 0.75f;
+            const float kx = tex_mix(K00.x, K10.x, K01.x, K11.x, ta, tb) * -0.72134752044448170368f;
+            const float ky = tex_mix(K00.y, K10.y, K01.y, K11.y, ta, tb) * -0.72134752044448170368f;
+            const float kz = tex_mix(K00.z, K10.z, K01.z, K11.z, ta, tb) * -0.72134752044448170368f;
+#pragma unroll
+            for (int py = 0; py <= 2; py++)
+#pragma unroll
+                for (int px = -2; px <= 2; px++) {
+                    if (py == 0 && px < 0) continue;
+                    const float q = (float)(px * px) * kx + (float)(2 * px * py) * kz + (float)(py * py) * ky;
+                    float e;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
+                    if (!(fabsf(e) < INFINITY)) e = (px * py == 0) ? 1.0f : 0.0f;      // :429-430
+                    wl[mt::widx(px, py)] = e;
+                }
+        }
+        for (int f = 0; f < A.n_frames; f++) {
+            const int2 s = shift_global(A, f, X, Y);
+            float ab[8];
+            generic_pixel(F, f, X, Y, s.x, s.y, wl, ab);
+#pragma unroll
+            for (int q = 0; q < 4; q++) { acc[q] += ab[q]; wacc[q] += ab[4 + q]; }
         }
     }
-    __syncthreads();
-    const bool border = s_border != 0;
-
-    // ---------------- phases 0 and 1 (independent of each other: the window origins are already known): interior tiles run the
-    // variant without clamp handling
-    if (border) stage_tile<TH, true>(F, smem, fbase, x0, y0, X0abs, Y0abs);
-    else stage_tile<TH, false>(F, smem, fbase, x0, y0, X0abs, Y0abs);
-    __syncthreads();
-
-    // ---------------- phase 2: warp w owns tile row w (Y % 4 == w % 4 == its scheduler): four passes J = 0..3
-    switch (warp & 3) {
-        case 0: run_rows<TH, 0>(F, smem, warp, x0, y0, X0abs, Y0abs); break;
-        case 1: run_rows<TH, 1>(F, smem, warp, x0, y0, X0abs, Y0abs); break;
-        case 2: run_rows<TH, 2>(F, smem, warp, x0, y0, X0abs, Y0abs); break;
-        default: run_rows<TH, 3>(F, smem, warp, x0, y0, X0abs, Y0abs); break;
+    float s3[3], w3[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        s3[c] = acc[0] * F.cfa_sel[0][c] + acc[1] * F.cfa_sel[1][c] + acc[2] * F.cfa_sel[2][c] + acc[3] * F.cfa_sel[3][c];
+        w3[c] = wacc[0] * F.cfa_sel[0][c] + wacc[1] * F.cfa_sel[1][c] + wacc[2] * F.cfa_sel[2][c] + wacc[3] * F.cfa_sel[3][c];
+    }
+    if (A.sum_in) {
+        const float* si = row_ptr(A.sum_in, A.acc_pitch, y) + 3 * x; const float* wi = row_ptr(A.weight_in, A.acc_pitch, y) + 3 * x;
+#pragma unroll
+        for (int c = 0; c < 3; c++) { s3[c] = si[c] + s3[c]; w3[c] = wi[c] + w3[c]; }
+    }
+    if (A.sum_out) {
+        float* so = row_ptr(A.sum_out, A.acc_pitch, y) + 3 * x; float* wo = row_ptr(A.weight_out, A.acc_pitch, y) + 3 * x;
+#pragma unroll
+        for (int c = 0; c < 3; c++) { so[c] = s3[c]; wo[c] = w3[c]; }
+    }
+    if (!(A.flags & MFSR_MERGE_PARTIAL_INTERNAL)) {
+        float fb3[3] = {0.f, 0.f, 0.f};
+        if (A.fallback) { const float* fp = row_ptr(A.fallback, A.fb_pitch, y) + 3 * x; fb3[0] = fp[0]; fb3[1] = fp[1]; fb3[2] = fp[2]; }
+        float* o = row_ptr(A.out, A.out_pitch, y) + 3 * x;
+#pragma unroll
+        for (int c = 0; c < 3; c++) o[c] = finish_px(apply_weighting(s3[c], w3[c], fb3[c], A.threshold), A.flags);
     }
 }
 
 template <int TH>
-int launch_th(const FastArgs& F, cudaStream_t st)
+int launch_th(const FastArgs& Fin, cudaStream_t st)
 {
     using C = PCfg<TH>;
+    FastArgs F = Fin;
     const mfsr_merge_geom& g = F.a.g;
     const size_t smem = C::smem_bytes(F.a.n_frames);
     // opt-in shared memory (227 KB per block on sm_100 minus this instantiation's static tables); the attribute belongs to the
@@ -622,8 +760,34 @@ int launch_th(const FastArgs& F, cudaStream_t st)
         max_dyn[dev] = lim;
     }
     if (smem > max_dyn[dev]) return MFSR_E_INVALID;
-    dim3 grid(cdiv(g.out_w + F.x_off, TW), cdiv(g.out_h + F.y_off, TH));
-    merge_pf_kernel<TH><<<grid, C::NT, smem, st>>>(F);
+    // interior rectangle of the window (window coordinates): pixels at least BAND HR pixels inside the clamp range and off the
+    // window's 1-pixel border; everything else is merge_band_kernel's
+    {
+        const int lox = 2 * g.clamp_x0 + 2, hix = 2 * g.clamp_x1 - 1, loy = 2 * g.clamp_y0 + 2, hiy = 2 * g.clamp_y1 - 1;
+        int ax0 = lox + BAND - g.org_x, ax1 = hix - BAND - g.org_x + 1, ay0 = loy + BAND - g.org_y, ay1 = hiy - BAND - g.org_y + 1;
+        ax0 = ax0 < 1 ? 1 : ax0; ay0 = ay0 < 1 ? 1 : ay0;
+        ax1 = ax1 > g.out_w - 1 ? g.out_w - 1 : ax1; ay1 = ay1 > g.out_h - 1 ? g.out_h - 1 : ay1;
+        if (ax1 <= ax0 || ay1 <= ay0) { ax0 = ax1 = 0; ay0 = 0; ay1 = 0; }          // no interior: the band kernel takes the whole window
+        F.in_x0 = ax0; F.in_x1 = ax1; F.in_y0 = ay0; F.in_y1 = ay1;
+    }
+    const int tiles_x = cdiv(g.out_w + F.x_off, TW), tiles_y = cdiv(g.out_h + F.y_off, TH);
+    static int n_sm[64] = {0};
+    if (!n_sm[dev]) MFSR_CUDA_TRY(cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev));
+    const int n_tiles = tiles_x * tiles_y;
+    if (F.in_x1 > F.in_x0) {
+        // one CTA per tile by default: the persistent grid (MFSR_PF_GRID=persistent: one CTA per SM walking the tiles with the next
+        // tile's lines prefetched to L2) measured 2.5 % slower — its per-tile barrier costs more than the prefetch saves
+        static const char* ge = getenv("MFSR_PF_GRID");
+        const bool full = !(ge && ge[0] == 'p');
+        merge_pf_kernel<TH><<<(full || n_tiles < n_sm[dev]) ? n_tiles : n_sm[dev], C::NT, smem, st>>>(F, tiles_x, n_tiles);
+        MFSR_LAUNCH_CHECK();
+    }
+    {
+        const int n_top = F.in_y0, n_mid = F.in_y1 - F.in_y0, n_left = F.in_x0, n_right = g.out_w - F.in_x1;
+        const long long total = (long long)(n_top + (g.out_h - F.in_y1)) * g.out_w + (long long)n_mid * (n_left + n_right);
+        if (total >= (1ll << 31)) return MFSR_E_INVALID;
+        if (total > 0) merge_band_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(F, n_top, n_mid, n_left, n_right, (int)total);
+    }
     MFSR_LAUNCH_CHECK();
     return MFSR_OK;
 }
@@ -634,7 +798,13 @@ int launch_th(const FastArgs& F, cudaStream_t st)
 namespace s2 {
 int merge_pf_capacity() { return (int)((227 * 1024 - 2048 - PCfg<16>::KERN_BYTES - PCfg<16>::TAB_BYTES) / (PCfg<16>::DESC_BYTES + PCfg<16>::RAW_BYTES + MASK_FRAME_BYTES)); }
 
-int launch_merge_pf(const FastArgs& F, cudaStream_t st) { return launch_th<16>(F, st); }
+int launch_merge_pf(const FastArgs& F, cudaStream_t st)
+{
+    static const char* e = getenv("MFSR_PF_TH");
+    const int th = e ? atoi(e) : 16;
+    if (th == 20) return launch_th<20>(F, st);
+    return launch_th<16>(F, st);
+}
 }  // namespace s2
 
 }  // namespace mfsr
