@@ -125,7 +125,12 @@ typedef struct mfsr_params {
      * it must cover the stencil footprints plus the largest vertical flow: 15 + 12 + max |flow_y| rows.  0 = whole band. */
     int   band_global_h, band_row0, band_keep_row0, band_keep_rows;
     int   band_margin;
-    int   reserved[3];
+    /* Global pre-alignment (PreAlignment skeleton boxFilterNPP.cpp:102-166): 1 = estimate one shift + rotation per
+     * frame against the reference frame (csrc/prealign.cu: exhaustive search over +-20 degrees and +-8 coarse pixels on two
+     * levels of the tracking pyramid) and feed it to the tile matcher and the flow field as their baseShift / baseRotation
+     * (kernel.cu:275-276, opticalFlow.cu:57-58) per pair / per frame; it then replaces base_shift / base_rotation.  0 = off. */
+    int   prealign;
+    int   reserved[2];
 } mfsr_params;
 
 int         mfsr_abi_version(void);
@@ -191,6 +196,13 @@ int mfsr_stage_tile_align(const uint8_t* ref, const uint8_t* mov, int64_t img_pi
                           float threshold, void* stream);
 
 /* UpSampleShifts (kernel.cu:642). */
+/* One stage of the global pre-alignment search on one image pair (8-bit tracking images of one pyramid level): candidates
+ * angle a = 0 .. n_ang-1 -> (cos, sin) = cs_table[idx0 + a*step] (device, n_table pairs), shift b = (cx, cy) + [-R, R]^2, every
+ * sub-th pixel; a reference pixel with centred coordinates c reads the moved image at p + round(R(theta)(c - b) - c) as
+ * kernel.cu:299-311 does.  out3 (device int[3]) = (a or -1, bx, by) of the candidate with the smallest mean squared difference. */
+int mfsr_stage_prealign_search(const uint8_t* ref, const uint8_t* mov, int64_t pitch, int width, int height,
+                               const float* cs_table, int n_table, int idx0, int step, int n_ang, int cx, int cy, int R, int sub,
+                               int* out3, void* stream);
 int mfsr_stage_upsample_shifts(const float* in_shift, int64_t in_pitch,
                                float* out_shift, int64_t out_pitch,
                                int oldLevel, int newLevel,

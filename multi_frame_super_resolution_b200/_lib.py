@@ -38,7 +38,7 @@ class Params(C.Structure):
         ("tensor_box_radius", c_i),
         ("alpha", c_f), ("beta", c_f), ("thresholdM", c_f), ("mask_erode_radius", c_i),
         ("weight_threshold", c_f), ("merge_flags", c_i),
-        ("band_global_h", c_i), ("band_row0", c_i), ("band_keep_row0", c_i), ("band_keep_rows", c_i), ("band_margin", c_i), ("reserved", c_i * 3),
+        ("band_global_h", c_i), ("band_row0", c_i), ("band_keep_row0", c_i), ("band_keep_rows", c_i), ("band_margin", c_i), ("prealign", c_i), ("reserved", c_i * 2),
     ]
 
 
@@ -76,6 +76,7 @@ SIGNATURES = {
     "mfsr_stage_pyramid_down": (c_i, [vp, c_i64, c_i, c_i, vp, c_i64, vp]),
     "mfsr_stage_tile_align": (c_i, [vp, vp, c_i64, c_i, c_i, vp, c_i64, vp, c_i64, vp, vp,
                                     c_i, c_i, c_i, c_i, c_f, c_f, c_f, c_f, vp]),
+    "mfsr_stage_prealign_search": (c_i, [vp, vp, c_i64, c_i, c_i, vp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, vp, vp]),
     "mfsr_stage_upsample_shifts": (c_i, [vp, c_i64, vp, c_i64, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, vp]),
     "mfsr_stage_consolidate_shifts": (c_i, [vp, ip, ip, c_i, c_i, c_i, c_i, c_i, vp, vp, vp, vp]),
     "mfsr_stage_flow_from_tiles": (c_i, [vp, c_i64, c_i, c_i, c_i, vp, c_i64, c_i, c_i, c_f, c_f, c_f, vp]),

@@ -30,7 +30,7 @@ FLAGS = [
 
 # Files whose fp32 results feed discrete decisions (quantisation, arg-min, rounding of tile
 # shifts) are compiled without FMA contraction so they round exactly like strict IEEE code.
-STRICT_FP = {"frontend.cu", "align.cu"}
+STRICT_FP = {"frontend.cu", "align.cu", "prealign.cu"}
 
 
 def _sources():

@@ -31,16 +31,26 @@ struct TileAlignArgs {
     float sf, cf;
 };
 
-// integer displacement of a tile (kernel.cu:299-311 / :358-370)
-__device__ __forceinline__ void tile_disp(const TileAlignArgs& A, int tix, int tiy, float prex, float prey, int& dx, int& dy)
+// integer displacement of a tile (kernel.cu:299-311 / :358-370).
+// Restated-host decision (round 2): the base shift / rotation is the pose of the MOVED image against the reference image, so
+// only the moved patches are displaced by it (convertToTilesOverlapPreShift, kernel.cu:324); the reference tiles
+// (convertToTilesOverlapBorder, :265) are taken with an identity base.  The reported tile shift is the RESIDUAL against the base
+// pose — coord + round(base + pre) - round(base) — which is what CreateFlowFieldFromTiles (opticalFlow.cu:72-86) adds to the
+// base displacement field.  (Round 1 displaced both patches, which cancels a base shift; with a zero base both forms coincide.)
+__device__ __forceinline__ void tile_disp(const TileAlignArgs& A, int pair, int tix, int tiy, float prex, float prey, int& dx, int& dy)
 {
+    float bsx = A.b.bsx, bsy = A.b.bsy, cf = A.cf, sf = A.sf;
+    if (A.b.pair_pose) {               // per-pair global pre-alignment (prealign.cu), shifts in full-resolution pixels
+        const float4 pp = *(const float4*)(A.b.pair_pose + 4 * pair);
+        bsx = pp.x * A.b.pose_scale; bsy = pp.y * A.b.pose_scale; cf = pp.z; sf = pp.w;
+    }
     float sx = prex, sy = prey;
-    sx += A.cf * -A.b.bsx - A.sf * -A.b.bsy;
-    sy += A.sf * -A.b.bsx + A.cf * -A.b.bsy;
+    sx += cf * -bsx - sf * -bsy;
+    sy += sf * -bsx + cf * -bsy;
     const float pcx = (float)(tix * A.b.T + A.b.T / 2 - A.b.w / 2);
     const float pcy = (float)(tiy * A.b.T + A.b.T / 2 - A.b.h / 2);
-    sx += A.cf * pcx - A.sf * pcy - pcx;
-    sy += A.sf * pcx + A.cf * pcy - pcy;
+    sx += cf * pcx - sf * pcy - pcx;
+    sy += sf * pcx + cf * pcy - pcy;
     dx = (int)roundf(sx); dy = (int)roundf(sy);
 }
 
@@ -72,8 +82,8 @@ tile_align_generic_kernel(const __grid_constant__ TileAlignArgs AA)
     float prex = 0.f, prey = 0.f;
     if (pre) { const float2 p = row_ptr(pre, B.pre_pitch, tiy)[tix]; prex = p.x; prey = p.y; }
     int dxm, dym, dxr, dyr;
-    tile_disp(A, tix, tiy, prex, prey, dxm, dym);
-    tile_disp(A, tix, tiy, 0.f, 0.f, dxr, dyr);
+    tile_disp(A, pair, tix, tiy, prex, prey, dxm, dym);
+    tile_disp(A, pair, tix, tiy, 0.f, 0.f, dxr, dyr);
 
     // gather patches (clamped like kernel.cu:312-313 / :371-372), pack 4 px per word
     for (int i = tid; i < P * PW; i += nthr) {
@@ -91,12 +101,12 @@ tile_align_generic_kernel(const __grid_constant__ TileAlignArgs AA)
     }
     for (int i = tid; i < T * TW; i += nthr) {
         const int py = i / TW, pw = i - py * TW;
-        const int gy = clampi(tiy * T + M + py + dyr, 0, B.h - 1);
+        const int gy = clampi(tiy * T + M + py, 0, B.h - 1);           // reference tiles are taken undisplaced (see tile_disp)
         const uint8_t* row = row_ptr(img_ref, B.pitch, gy);
         uint32_t v = 0;
 #pragma unroll
         for (int b = 0; b < 4; b++) {
-            const int gx = clampi(tix * T + M + pw * 4 + b + dxr, 0, B.w - 1);
+            const int gx = clampi(tix * T + M + pw * 4 + b, 0, B.w - 1);
             v |= (uint32_t)row[gx] << (8 * b);
         }
         s_ref[i] = v;
@@ -292,8 +302,8 @@ tile_align16_kernel(const __grid_constant__ TileAlignArgs AA)
     float prex = 0.f, prey = 0.f;
     if (pre) { const float2 p = row_ptr(pre, B.pre_pitch, tiy)[tix]; prex = p.x; prey = p.y; }
     int dxm, dym, dxr, dyr;
-    tile_disp(A, tix, tiy, prex, prey, dxm, dym);
-    tile_disp(A, tix, tiy, 0.f, 0.f, dxr, dyr);
+    tile_disp(A, pair, tix, tiy, prex, prey, dxm, dym);
+    tile_disp(A, pair, tix, tiy, 0.f, 0.f, dxr, dyr);
 
     // ---- moved patch (clamped like kernel.cu:371-372)
     const int gxs = tix * T + dxm, gys = tiy * T + dym;
@@ -319,7 +329,7 @@ tile_align16_kernel(const __grid_constant__ TileAlignArgs AA)
         }
     }
     // ---- template patch (kernel.cu:312-313), exact alignment
-    const int gxr = tix * T + M + dxr, gyr = tiy * T + M + dyr;
+    const int gxr = tix * T + M, gyr = tiy * T + M;                        // reference tiles are taken undisplaced (see tile_disp)
     const bool rfast = gxr >= 0 && gxr + T <= B.w && (int64_t)((gxr & ~3) + T + 4) <= B.pitch;
     for (int i = lane; i < T * TW; i += 32) {
         const int py = i >> 2, xw = i & 3;
@@ -501,7 +511,8 @@ consolidate_inverse_kernel(PairTable pt, int m, int imageCount, float* __restric
 
 __global__ void __launch_bounds__(128)
 consolidate_kernel(const float2* __restrict__ measured, int64_t tile_stride, int64_t pair_stride, PairTable pt, int m, int imageCount, int nTiles, int referenceImage,
-                   float2* __restrict__ one_to_one, float2* __restrict__ frame_shift, int* __restrict__ status, const float* __restrict__ inv0)
+                   float2* __restrict__ one_to_one, float2* __restrict__ frame_shift, int* __restrict__ status, const float* __restrict__ inv0,
+                   const unsigned long long* __restrict__ active0)
 {
     extern __shared__ float cs[];
     const int n1 = imageCount - 1;
@@ -515,12 +526,17 @@ consolidate_kernel(const float2* __restrict__ measured, int64_t tile_stride, int
     float* x = atb + 2 * n1;                  // [n1][2]
     if (t >= nTiles) return;
     for (int k = lane; k < m; k += 32) { const float2 v = measured[(int64_t)t * tile_stride + (int64_t)k * pair_stride]; b[2 * k] = v.x; b[2 * k + 1] = v.y; }
-    unsigned long long active = (m >= 64) ? ~0ull : ((1ull << m) - 1ull);
+    const unsigned long long full = (m >= 64) ? ~0ull : ((1ull << m) - 1ull);
+    // pairs the global pre-alignment ruled out (relative rotation too large for translation-only tile matching, prealign.cu) start removed
+    unsigned long long active = active0 ? (*active0 & full) : full;
+    __syncwarp();
+    if (active != full)
+        for (int k = lane; k < m; k += 32) if (!((active >> k) & 1ull)) { b[2 * k] = 0.f; b[2 * k + 1] = 0.f; }
     int removed = 0, st = 0;
     __syncwarp();
     for (;;) {
         bool singular;
-        if (removed == 0 && inv0 && inv0[n1 * n1] != 0.0f) {       // the full system: inverted once per burst
+        if (removed == 0 && active == full && inv0 && inv0[n1 * n1] != 0.0f) {       // the full system: inverted once per burst
             for (int e = lane; e < n1 * n1; e += 32) inv[e] = inv0[e];
             singular = false;
             __syncwarp();
@@ -615,7 +631,7 @@ int mfsr::launch_upsample_shifts(const UpsampleBatch& u, cudaStream_t st)
 
 int mfsr::launch_consolidate(const float2* measured, int64_t tile_stride, int64_t pair_stride, const PairTable& pt, int m,
                              int imageCount, int nTiles, int referenceImage, float2* one_to_one, float2* frame_shift,
-                             int* status, float* inv0_scratch, cudaStream_t st)
+                             int* status, float* inv0_scratch, cudaStream_t st, const unsigned long long* active0)
 {
     const int n1 = imageCount - 1, warps = 4;
     const size_t smem = (size_t)warps * (2 * n1 * n1 + 2 * m + 4 * n1) * sizeof(float);
@@ -626,7 +642,7 @@ int mfsr::launch_consolidate(const float2* measured, int64_t tile_stride, int64_
         MFSR_LAUNCH_CHECK();
     }
     consolidate_kernel<<<cdiv(nTiles, warps), warps * 32, smem, st>>>(measured, tile_stride, pair_stride, pt, m, imageCount, nTiles,
-                                                                    referenceImage, one_to_one, frame_shift, status, inv0_scratch);
+                                                                    referenceImage, one_to_one, frame_shift, status, inv0_scratch, active0);
     MFSR_LAUNCH_CHECK();
     return MFSR_OK;
 }

@@ -18,8 +18,9 @@ constexpr int FFT_ROWS = 8;      // rows per thread: the column-only part (textu
 __global__ void __launch_bounds__(256)
 flow_from_tiles_kernel(const float2* __restrict__ tiles, int64_t tile_pitch, int tilesX, int tilesY,
                        float2* __restrict__ flow, int64_t flow_pitch, int w, int h, float bsx, float bsy, float cr, float sr,
-                       int gh, int gy0, int gty, int trow0)
+                       int gh, int gy0, int gty, int trow0, const float* __restrict__ frame_pose)
 {
+    if (frame_pose) { bsx = frame_pose[0]; bsy = frame_pose[1]; cr = frame_pose[2]; sr = frame_pose[3]; }      // prealign.cu
     const int x = blockIdx.x * blockDim.x + threadIdx.x, yb = (blockIdx.y * blockDim.y + threadIdx.y) * FFT_ROWS;
     if (x >= w || yb >= h) return;
     const float bx = cr * -bsx - sr * -bsy, by = sr * -bsx + cr * -bsy;
@@ -281,12 +282,12 @@ lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov
 using namespace mfsr;
 
 int mfsr::launch_flow_from_tiles(const float2* tiles, int64_t tile_pitch, int tilesX, int tilesY, float2* flow, int64_t flow_pitch, int w, int h,
-                                 float bsx, float bsy, float rot, int gh, int gy0, int gty, int tile_row0, cudaStream_t st)
+                                 float bsx, float bsy, float rot, int gh, int gy0, int gty, int tile_row0, cudaStream_t st, const float* frame_pose)
 {
     if (!tiles || !flow || tilesX < 1 || tilesY < 1 || w < 1 || h < 1) return MFSR_E_INVALID;
     if (gh <= 0) { gh = h; gy0 = 0; gty = tilesY; tile_row0 = 0; }
     dim3 b(32, 8), g(cdiv(w, 32), cdiv(h, 8 * FFT_ROWS));
-    flow_from_tiles_kernel<<<g, b, 0, st>>>(tiles, tile_pitch, tilesX, tilesY, flow, flow_pitch, w, h, bsx, bsy, cosf(rot), sinf(rot), gh, gy0, gty, tile_row0);
+    flow_from_tiles_kernel<<<g, b, 0, st>>>(tiles, tile_pitch, tilesX, tilesY, flow, flow_pitch, w, h, bsx, bsy, cosf(rot), sinf(rot), gh, gy0, gty, tile_row0, frame_pose);
     MFSR_LAUNCH_CHECK();
     return MFSR_OK;
 }

@@ -19,6 +19,9 @@ struct TileAlignBatch {
     PairTable pt; int n_pairs;
     int T, M, tx, ty;
     float bsx, bsy, rot, threshold;
+    // global pre-alignment (prealign.cu): per pair (shift x, shift y in full-resolution pixels, cos, sin) on the device, or null;
+    // when given it replaces bsx / bsy / rot.  pose_scale = 1 / 2^level.
+    const float* pair_pose; float pose_scale;
 };
 int launch_tile_align(const TileAlignBatch& b, cudaStream_t st);
 
@@ -32,13 +35,23 @@ int launch_upsample_shifts(const UpsampleBatch& b, cudaStream_t st);
 // measured element (tile t, pair k) at measured[t*tile_stride + k*pair_stride] (in float2 units)
 int launch_consolidate(const float2* measured, int64_t tile_stride, int64_t pair_stride, const PairTable& pt, int m,
                        int imageCount, int nTiles, int referenceImage, float2* one_to_one, float2* frame_shift,
-                       int* status, float* inv0_scratch, cudaStream_t st);      // inv0_scratch: (n-1)^2 + 1 floats or null
+                       int* status, float* inv0_scratch, cudaStream_t st,       // inv0_scratch: (n-1)^2 + 1 floats or null
+                       const unsigned long long* active0 = nullptr);            // device: bit k = pair k takes part (null: all)
 
 // CreateFlowFieldFromTiles for a row band: pixel rows and tile rows are mapped through the FULL frame's normalised texture
 // coordinates (global height gh, global tile rows gty; local row 0 is global row gy0, local tile row 0 is global tile row
 // gy0 / T) so that a band reproduces the full-frame flow.  gh == 0: plain local mapping.
 int launch_flow_from_tiles(const float2* tiles, int64_t tile_pitch, int tilesX, int tilesY, float2* flow, int64_t flow_pitch, int w, int h,
-                           float bsx, float bsy, float rot, int gh, int gy0, int gty, int tile_row0, cudaStream_t st);
+                           float bsx, float bsy, float rot, int gh, int gy0, int gty, int tile_row0, cudaStream_t st,
+                           const float* frame_pose = nullptr);      // frame_pose: device (bx, by, cos, sin) replacing bsx / bsy / rot
+
+// global pre-alignment (prealign.cu)
+int launch_prealign_stage(const uint8_t* img, int64_t pitch, int64_t frame_stride, int w, int h, int n_frames, int ref_idx,
+                          const float* cs, int zero_idx, void* fs_in, int step, int n_ang, int R, int sub,
+                          unsigned long long* ssd, unsigned* cnt, int* result3,
+                          void* fs_next, int next_scale, int next_half, int next_step, float* pose, int pose_scale, cudaStream_t st);
+int launch_prealign_init(void* fs, int n, int idx0, cudaStream_t st);
+int launch_pair_pose(const float* pose, const PairTable& pt, int m, float* pair_pose, unsigned long long* pair_valid, cudaStream_t st);
 
 // one Lucas-Kanade sweep; gh / gy0 as above (0: whole frame)
 int launch_lk_iteration(const float* ref, const float* mov, int64_t img_pitch, const float2* flow_in, float2* flow_out, int64_t flow_pitch,

@@ -10,6 +10,7 @@
 #include <new>
 #include <string.h>
 #include <vector>
+#include <math.h>
 
 using namespace mfsr;
 
@@ -19,6 +20,11 @@ enum Stage { ST_UPLOAD, ST_FRONTEND, ST_ALIGN, ST_CONSOLIDATE, ST_FLOW, ST_KERNE
 const char* kStageNames[ST_COUNT] = {"upload", "frontend", "align", "consolidate", "flow", "kernel_params", "robustness", "fallback", "merge", "download"};
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// global pre-alignment search (prealign.cu): angle table of 0.125 degree steps over +-21 degrees
+constexpr int PA_FINE = 8, PA_MAXDEG = 21, PA_TABLE = 2 * PA_MAXDEG * PA_FINE + 1, PA_ZERO = PA_MAXDEG * PA_FINE;
+constexpr int PA_A_DEG = 20, PA_A_ANG = 2 * PA_A_DEG + 1, PA_A_R = 8, PA_B_HALF = 8, PA_B_ANG = 2 * PA_B_HALF + 1, PA_B_R = 4, PA_B_SUB = 2;
+constexpr int PA_SMALL = 192;
 
 struct Level { int w, h, tx, ty; int64_t pitch, frame_stride; uint8_t* img; float2* shift; float2* pre; };
 
@@ -51,6 +57,12 @@ struct mfsr_context {
     PairTable pt; int m;
     int2* argmin; float2* one_to_one; float2* frame_shift; int* cons_status; float* cons_inv0;
     float2* flow_final;   // which of flowA/flowB holds the final flow
+    // global pre-alignment (prealign.cu): extra pyramid levels below the matcher's, search scratch, poses
+    std::vector<Level> pal;                             // levels lv.size() .. of the tracking pyramid (img only)
+    int pa_la, pa_lb;                                   // search levels of stages A and B (global level numbers)
+    float* pa_cs; char* pa_scratch; size_t pa_scratch_bytes;
+    float* pose; float* pair_pose; int* pa_result;      // per frame (bx, by, cos, sin); per pair; per frame and stage (a, bx, by)
+    unsigned long long* pair_valid;                     // bit k: pair k takes part in the shift consolidation
     mfsr_merge_geom geom;
 };
 
@@ -148,12 +160,29 @@ static int validate_params(const mfsr_params* p)
     if (p->lk_iterations < 0 || p->lk_half_window < 1 || p->lk_half_window > 4) return MFSR_E_INVALID;
     if (p->tensor_box_radius < 0 || p->tensor_box_radius > 3 || p->mask_erode_radius < 0 || p->mask_erode_radius > 8) return MFSR_E_INVALID;
     for (int i = 0; i < 4; i++) if (p->cfa[i] < 0 || p->cfa[i] > 2) return MFSR_E_INVALID;
+    if (p->prealign != 0 && p->prealign != 1) return MFSR_E_INVALID;
     if (p->band_global_h < 0 || p->band_row0 < 0 || p->band_keep_row0 < 0 || p->band_keep_rows < 0 || p->band_margin < 0) return MFSR_E_INVALID;
     if (p->band_global_h > 0) {
         const int grid = p->tile_size << (p->levels - 1);
-        if (!p->full_frame || p->base_rotation != 0.0f || (p->band_row0 % grid) || p->band_row0 >= p->band_global_h) return MFSR_E_INVALID;
+        if (!p->full_frame || p->base_rotation != 0.0f || p->prealign || (p->band_row0 % grid) || p->band_row0 >= p->band_global_h) return MFSR_E_INVALID;
     }
     return MFSR_OK;
+}
+
+// measured pairs (i, j), i < j: every pair at most pair_span frames apart; with the global pre-alignment also every frame
+// against the reference frame (distant frames may be rotated too far against their neighbours to be matched, prealign.cu).
+// Lexicographic order.  Returns the count; fills from / to when given.
+static int build_pairs(const mfsr_params& p, int n, int ref_idx, int8_t* from, int8_t* to, int cap)
+{
+    int m = 0;
+    for (int i = 0; i < n; i++)
+        for (int j = i + 1; j < n; j++) {
+            const bool take = (j - i <= p.pair_span) || (p.prealign && (i == ref_idx || j == ref_idx));
+            if (!take) continue;
+            if (from && m < cap) { from[m] = (int8_t)i; to[m] = (int8_t)j; }
+            m++;
+        }
+    return m;
 }
 
 // carve the workspace; returns required bytes. If base == nullptr only measures.
@@ -188,9 +217,9 @@ static size_t carve(mfsr_context* c, char* base, int n, int w, int h)
         c->part_sum = (float*)take((size_t)c->out_pitch_own * (g.out_h + 2));
         c->part_weight = (float*)take((size_t)c->out_pitch_own * (g.out_h + 2));
     }
-    // measured pairs
-    int m = 0;
-    for (int i = 0; i < n; i++) for (int j = i + 1; j < n && j - i <= p.pair_span; j++) m++;
+    // measured pairs (upper bound over the possible reference frames when pre-aligning)
+    int m = build_pairs(p, n, 0, nullptr, nullptr, 0);
+    if (p.prealign) for (int r = 1; r < n; r++) { const int mr = build_pairs(p, n, r, nullptr, nullptr, 0); if (mr > m) m = mr; }
     if (m < 1) m = 1;
     // pyramid
     c->lv.clear();
@@ -205,6 +234,28 @@ static size_t carve(mfsr_context* c, char* base, int n, int w, int h)
         L.pre = (float2*)take((size_t)L.tx * L.ty * 8 * m);
         c->lv.push_back(L);
         lw /= 2; lh /= 2;
+    }
+    // global pre-alignment: the tracking pyramid continues below the matcher's levels until the longer side is <= PA_SMALL
+    c->pal.clear(); c->pa_la = c->pa_lb = 0; c->pa_cs = nullptr; c->pa_scratch = nullptr; c->pose = c->pair_pose = nullptr; c->pa_result = nullptr; c->pair_valid = nullptr;
+    if (p.prealign && !c->lv.empty()) {
+        int la = 0, aw = w, ah = h;
+        while ((aw > PA_SMALL || ah > PA_SMALL) && aw / 2 >= 16 && ah / 2 >= 16) { aw /= 2; ah /= 2; la++; }
+        c->pa_la = la; c->pa_lb = la >= 2 ? la - 2 : 0;
+        int pw = c->lv.back().w, ph = c->lv.back().h;
+        for (int l = (int)c->lv.size(); l <= la; l++) {
+            pw /= 2; ph /= 2;
+            Level L = {}; L.w = pw; L.h = ph; L.pitch = align_up((size_t)pw, 16); L.frame_stride = L.pitch * ph;
+            L.img = (uint8_t*)take((size_t)L.frame_stride * n);
+            c->pal.push_back(L);
+        }
+        c->pa_cs = (float*)take((size_t)PA_TABLE * 8);
+        const size_t ncand = (size_t)PA_A_ANG * (2 * PA_A_R + 1) * (2 * PA_A_R + 1);
+        c->pa_scratch_bytes = (size_t)n * ncand * 12 + (size_t)n * 2 * 16;
+        c->pa_scratch = take(c->pa_scratch_bytes);
+        c->pose = (float*)take((size_t)n * 16);
+        c->pair_pose = (float*)take((size_t)m * 16);
+        c->pa_result = (int*)take((size_t)n * 2 * 12);
+        c->pair_valid = (unsigned long long*)take(8);
     }
     if (!c->lv.empty()) {
         const size_t nt = (size_t)c->lv[0].tx * c->lv[0].ty;
@@ -283,21 +334,32 @@ extern "C" int mfsr_set_frames(mfsr_handle h, const void* const* frames, int n, 
     if (!h || !frames || n < 1 || n > h->max_frames || width > h->max_w || height > h->max_h) return MFSR_E_INVALID;
     if (width < 64 || height < 64 || (width & 1) || (height & 1) || ref_idx < 0 || ref_idx >= n || pitch < (int64_t)width * 2) return MFSR_E_INVALID;
     if (format != MFSR_FMT_BAYER_U16 && format != MFSR_FMT_GRAY_U16) return MFSR_E_INVALID;
+    // everything that can be rejected is checked BEFORE the handle's state changes (a failed call leaves no half-configured burst)
+    for (int f = 0; f < n; f++)
+        if (!frames[f]) return MFSR_E_INVALID;
+    if (build_pairs(h->p, n, ref_idx, nullptr, nullptr, 0) > CONS_MAX_M) return MFSR_E_INVALID;
+    h->have_frames = false; h->ran = false;
     MFSR_CUDA_TRY(cudaSetDevice(h->device));
     carve(h, h->ws, n, width, height);
     if (h->lv.empty()) return MFSR_E_INVALID;
     h->n = n; h->w = width; h->h = height; h->ref_idx = ref_idx; h->format = format;
     make_geom(h->p, width, height, &h->geom);
     // measured pairs (i, j), 0 < j - i <= pair_span
-    h->m = 0;
-    for (int i = 0; i < n; i++)
-        for (int j = i + 1; j < n && j - i <= h->p.pair_span; j++) {
-            if (h->m >= CONS_MAX_M) return MFSR_E_INVALID;
-            h->pt.from[h->m] = (int8_t)i; h->pt.to[h->m] = (int8_t)j; h->m++;
+    h->m = build_pairs(h->p, n, ref_idx, h->pt.from, h->pt.to, CONS_MAX_M);
+    if (h->pa_cs) {
+        // (cos, sin) of the candidate angles, computed in double and rounded once: the oracle uses the same table
+        static float table[2 * PA_TABLE];
+        static bool filled = false;
+        if (!filled) {
+            for (int i = 0; i < PA_TABLE; i++) {
+                const double th = (double)(i - PA_ZERO) * (0.125 * 3.14159265358979323846 / 180.0);
+                table[2 * i] = (float)cos(th); table[2 * i + 1] = (float)sin(th);
+            }
+            filled = true;
         }
+        MFSR_CUDA_TRY(cudaMemcpyAsync(h->pa_cs, table, sizeof(table), cudaMemcpyHostToDevice, h->stream));
+    }
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_UPLOAD], h->stream));
-    for (int f = 0; f < n; f++)
-        if (!frames[f]) return MFSR_E_INVALID;
     // Device frames that form an evenly spaced, vector-load-aligned stack are used IN PLACE (no staging copy);
     // the caller keeps them alive until the run has finished.  Anything else is copied into the workspace.
     bool in_place = !on_host && !((uintptr_t)frames[0] & 15) && !(pitch & 15);
@@ -366,6 +428,34 @@ static int run_impl(mfsr_handle h, void* out_any, int64_t out_pitch, int out_on_
     // ---- C. pyramid tile matching, all measured pairs per launch, coarse -> fine
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_ALIGN], st));
     const int L = (int)h->lv.size();
+    const bool pre = p.prealign && n > 1 && h->pose;
+    if (pre) {
+        // ---- B. global pre-alignment: tracking pyramid below the matcher's levels, two exhaustive search stages, poses per frame / pair
+        auto level_img = [&](int l, const uint8_t*& img, int64_t& pitch, int64_t& fstride, int& lw, int& lh) {
+            const Level& V = l < L ? h->lv[l] : h->pal[l - L];
+            img = V.img; pitch = V.pitch; fstride = V.frame_stride; lw = V.w; lh = V.h;
+        };
+        for (size_t k = 0; k < h->pal.size(); k++) {
+            const Level& src = k == 0 ? h->lv.back() : h->pal[k - 1];
+            for (int f = 0; f < n; f++)
+                RUN(mfsr_stage_pyramid_down(src.img + src.frame_stride * f, src.pitch, src.w, src.h, h->pal[k].img + h->pal[k].frame_stride * f, h->pal[k].pitch, st));
+        }
+        const size_t ncandA = (size_t)PA_A_ANG * (2 * PA_A_R + 1) * (2 * PA_A_R + 1);
+        unsigned long long* ssd = (unsigned long long*)h->pa_scratch;
+        unsigned* cnt = (unsigned*)(h->pa_scratch + (size_t)n * ncandA * 8);
+        char* fsA = h->pa_scratch + (size_t)n * ncandA * 12; char* fsB = fsA + (size_t)n * 16;
+        const uint8_t* img; int64_t pitch, fstride; int lw, lh;
+        RUN(launch_prealign_init(fsA, n, PA_ZERO - PA_A_DEG * PA_FINE, st));
+        level_img(h->pa_la, img, pitch, fstride, lw, lh);
+        RUN(launch_prealign_stage(img, pitch, fstride, lw, lh, n, h->ref_idx, h->pa_cs, PA_ZERO, fsA, PA_FINE, PA_A_ANG, PA_A_R, 1, ssd, cnt, h->pa_result,
+                                  fsB, 1 << (h->pa_la - h->pa_lb), PA_B_HALF, 1, nullptr, 1, st));
+        h->launches++;
+        level_img(h->pa_lb, img, pitch, fstride, lw, lh);
+        RUN(launch_prealign_stage(img, pitch, fstride, lw, lh, n, h->ref_idx, h->pa_cs, PA_ZERO, fsB, 1, PA_B_ANG, PA_B_R, PA_B_SUB, ssd, cnt, h->pa_result + 3 * n,
+                                  nullptr, 1, 0, 1, h->pose, 1 << h->pa_lb, st));
+        h->launches++;
+        RUN(launch_pair_pose(h->pose, h->pt, h->m, h->pair_pose, h->pair_valid, st));
+    }
     if (n > 1) {
         for (int l = L - 1; l >= 0; l--) {
             Level& V = h->lv[l];
@@ -389,6 +479,7 @@ static int run_impl(mfsr_handle h, void* out_any, int64_t out_pitch, int out_on_
             // the global pre-alignment is expressed in full-resolution pixels
             b.bsx = p.base_shift[0] / (float)(1 << l); b.bsy = p.base_shift[1] / (float)(1 << l); b.rot = p.base_rotation;
             b.threshold = p.min_threshold;
+            b.pair_pose = pre ? h->pair_pose : nullptr; b.pose_scale = 1.0f / (float)(1 << l);
             RUN(launch_tile_align(b, st));
         }
     }
@@ -396,7 +487,7 @@ static int run_impl(mfsr_handle h, void* out_any, int64_t out_pitch, int out_on_
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_CONSOLIDATE], st));
     const int tx = h->lv[0].tx, ty = h->lv[0].ty, nt = tx * ty;
     if (n > 1) {
-        RUN(launch_consolidate(h->lv[0].shift, 1, nt, h->pt, h->m, n, nt, h->ref_idx, h->one_to_one, h->frame_shift, h->cons_status, h->cons_inv0, st));
+        RUN(launch_consolidate(h->lv[0].shift, 1, nt, h->pt, h->m, n, nt, h->ref_idx, h->one_to_one, h->frame_shift, h->cons_status, h->cons_inv0, st, pre ? h->pair_valid : nullptr));
     } else {
         MFSR_CUDA_TRY(cudaMemsetAsync(h->frame_shift, 0, (size_t)nt * 8, st));
     }
@@ -420,7 +511,8 @@ static int run_impl(mfsr_handle h, void* out_any, int64_t out_pitch, int out_on_
     for (int f = 0; f < n; f++)
         RUN(launch_flow_from_tiles(h->frame_shift + (size_t)f * nt, (int64_t)tx * 8, tx, ty,
                                    (float2*)((char*)cur + h->flow_fs * f + h->flow_pitch * ra), h->flow_pitch,
-                                   w, rh, p.base_shift[0], p.base_shift[1], p.base_rotation, gh, gy0, gty, p.band_row0 / p.tile_size, st));
+                                   w, rh, p.base_shift[0], p.base_shift[1], p.base_rotation, gh, gy0, gty, p.band_row0 / p.tile_size, st,
+                                   pre ? h->pose + 4 * f : nullptr));
     for (int it = 0; it < p.lk_iterations; it++) {
         for (int f = 0; f < n; f++) {
             if (f == h->ref_idx) {   // reference against itself: Iz == 0 -> UV == 0, flow unchanged
@@ -565,6 +657,8 @@ extern "C" int mfsr_get_buffer(mfsr_handle h, const char* name, void** dev_ptr, 
     else if (!strcmp(name, "mask")) { p = h->mask; pi = h->mask_pitch; fs = h->mask_fs; }
     else if (!strcmp(name, "kernel")) { p = h->kern; pi = h->kern_pitch; fs = 0; }
     else if (!strcmp(name, "fallback")) { p = h->fallback; pi = h->out_pitch_own; fs = 0; }
+    else if (!strcmp(name, "pose")) { if (!h->pose || !h->ran) return MFSR_E_STATE; p = h->pose; pi = 16; fs = 16; }
+    else if (!strcmp(name, "prealign_result")) { if (!h->pa_result || !h->ran) return MFSR_E_STATE; p = h->pa_result; pi = 12; fs = 12; }
     else if (!strcmp(name, "tile_shift0")) { p = h->lv[0].shift; pi = (int64_t)h->lv[0].tx * 8; fs = (int64_t)h->lv[0].tx * h->lv[0].ty * 8; }
     else return MFSR_E_INVALID;
     *dev_ptr = p;

@@ -46,9 +46,11 @@ def default_params() -> Params:
     return p
 
 
-def measured_pairs(n_frames: int, pair_span: int):
-    """The (from, to) frame pairs the aligner measures: 0 < to - from <= pair_span."""
-    return [(i, j) for i in range(n_frames) for j in range(i + 1, min(n_frames, i + pair_span + 1))]
+def measured_pairs(n_frames: int, pair_span: int, prealign: int = 0, ref_idx: int = 0):
+    """The (from, to) frame pairs the aligner measures: 0 < to - from <= pair_span, with the global pre-alignment also every
+    frame against the reference frame (csrc/pipeline.cu: build_pairs)."""
+    return [(i, j) for i in range(n_frames) for j in range(i + 1, n_frames)
+            if j - i <= pair_span or (prealign and (i == ref_idx or j == ref_idx))]
 
 
 class BurstSuperResolution:

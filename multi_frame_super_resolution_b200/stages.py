@@ -87,6 +87,26 @@ def tile_align(ref, mov, pre_shift=None, tile_size=16, max_shift=4, base_shift=(
     return out, arg, ssd
 
 
+def prealign_table():
+    """(cos, sin) of the candidate angles of the global pre-alignment: 0.125 degree steps over +-21 degrees, computed in double and
+    rounded once (pipeline.cu uploads the same table).  Returns (float32 [337, 2], index of angle 0)."""
+    import numpy as np
+    i = np.arange(2 * 21 * 8 + 1, dtype=np.float64) - 21 * 8
+    th = i * (0.125 * 3.14159265358979323846 / 180.0)
+    return np.stack([np.cos(th), np.sin(th)], axis=1).astype(np.float32), 21 * 8
+
+
+def prealign_search(ref, mov, cs_table, idx0, step, n_ang, cx=0, cy=0, radius=8, sub=1):
+    """One stage of the global pre-alignment search (csrc/prealign.cu) on a pair of 8-bit tracking images.  Returns int32 [3] =
+    (angle candidate or -1, bx, by)."""
+    _cuda(ref, mov, cs_table)
+    h, w = ref.shape
+    out = torch.zeros((3,), dtype=torch.int32, device=ref.device)
+    check(_lib.load().mfsr_stage_prealign_search(_p(ref), _p(mov), ref.stride(0), w, h, _p(cs_table), cs_table.shape[0], idx0, step, n_ang,
+                                                 cx, cy, radius, sub, _p(out), _stream()), "mfsr_stage_prealign_search")
+    return out
+
+
 def upsample_shifts(in_shift, old_level, new_level, new_cx, new_cy, old_t, new_t):
     _cuda(in_shift)
     ocy, ocx = in_shift.shape[:2]

@@ -228,9 +228,8 @@ void orc_pyramid_down(const uint8_t* in, int in_w, int in_h, uint8_t* out)
 }
 
 /* ---- kernel.cu:265 / :324 tile extraction ------------------------------- */
-static void tile_disp(int tix, int tiy, int T, int w, int h, float prex, float prey, float bsx, float bsy, float rot, int* dx, int* dy)
+static void tile_disp(int tix, int tiy, int T, int w, int h, float prex, float prey, float bsx, float bsy, float cf, float sf, int* dx, int* dy)
 {
-    float sf = sinf(rot), cf = cosf(rot);
     float sx = prex, sy = prey;
     sx += cf * -bsx - sf * -bsy;
     sy += sf * -bsx + cf * -bsy;
@@ -240,13 +239,13 @@ static void tile_disp(int tix, int tiy, int T, int w, int h, float prex, float p
     sy += sf * pcx + cf * pcy - pcy;
     *dx = (int)roundf(sx); *dy = (int)roundf(sy);
 }
-void orc_tiles_border(const float* img, float* tiles, int w, int h, int M, int T, int tx, int ty, float bsx, float bsy, float rot)
+static void tiles_border_cs(const float* img, float* tiles, int w, int h, int M, int T, int tx, int ty, float bsx, float bsy, float cf, float sf)
 {
     int P = T + 2 * M;
 #pragma omp parallel for schedule(static)
     for (int t = 0; t < tx * ty; t++) {
         int tiy = t / tx, tix = t - tiy * tx, dx, dy;
-        tile_disp(tix, tiy, T, w, h, 0.0f, 0.0f, bsx, bsy, rot, &dx, &dy);
+        tile_disp(tix, tiy, T, w, h, 0.0f, 0.0f, bsx, bsy, cf, sf, &dx, &dy);
         for (int py = 0; py < P; py++)
             for (int px = 0; px < P; px++) {
                 float v = 0;
@@ -259,14 +258,18 @@ void orc_tiles_border(const float* img, float* tiles, int w, int h, int M, int T
             }
     }
 }
-void orc_tiles_preshift(const float* img, float* tiles, const float* pre2, int w, int h, int M, int T, int tx, int ty, float bsx, float bsy, float rot)
+void orc_tiles_border(const float* img, float* tiles, int w, int h, int M, int T, int tx, int ty, float bsx, float bsy, float rot)
+{
+    tiles_border_cs(img, tiles, w, h, M, T, tx, ty, bsx, bsy, cosf(rot), sinf(rot));
+}
+static void tiles_preshift_cs(const float* img, float* tiles, const float* pre2, int w, int h, int M, int T, int tx, int ty, float bsx, float bsy, float cf, float sf)
 {
     int P = T + 2 * M;
 #pragma omp parallel for schedule(static)
     for (int t = 0; t < tx * ty; t++) {
         int tiy = t / tx, tix = t - tiy * tx, dx, dy;
         float prx = pre2 ? pre2[2 * t] : 0.0f, pry = pre2 ? pre2[2 * t + 1] : 0.0f;
-        tile_disp(tix, tiy, T, w, h, prx, pry, bsx, bsy, rot, &dx, &dy);
+        tile_disp(tix, tiy, T, w, h, prx, pry, bsx, bsy, cf, sf, &dx, &dy);
         for (int py = 0; py < P; py++)
             for (int px = 0; px < P; px++) {
                 int ix = (int)fminf(fmaxf((float)(tix * T + px + dx), 0), (float)(w - 1));
@@ -274,6 +277,10 @@ void orc_tiles_preshift(const float* img, float* tiles, const float* pre2, int w
                 tiles[((size_t)t * P + py) * P + px] = img[(size_t)iy * w + ix];
             }
     }
+}
+void orc_tiles_preshift(const float* img, float* tiles, const float* pre2, int w, int h, int M, int T, int tx, int ty, float bsx, float bsy, float rot)
+{
+    tiles_preshift_cs(img, tiles, pre2, w, h, M, T, tx, ty, bsx, bsy, cosf(rot), sinf(rot));
 }
 
 /* Circular cross-correlation cc[s] = sum_p a[p] * b[(p+s) mod P]  (what
@@ -435,9 +442,9 @@ void orc_find_minimum(const float* ssd, float* coord2, int32_t* argmin2, int M, 
     }
 }
 
-void orc_tile_align(const uint8_t* ref, const uint8_t* mov, int w, int h, const float* pre2,
-                    float* out_shift2, int32_t* argmin2, float* ssd_out,
-                    int T, int M, int tx, int ty, float bsx, float bsy, float rot, float threshold)
+void orc_tile_align_cs(const uint8_t* ref, const uint8_t* mov, int w, int h, const float* pre2,
+                       float* out_shift2, int32_t* argmin2, float* ssd_out,
+                       int T, int M, int tx, int ty, float bsx, float bsy, float cf, float sf, float threshold)
 {
     int P = T + 2 * M, S = 2 * M + 1, nt = tx * ty;
     size_t npx = (size_t)w * h;
@@ -451,8 +458,9 @@ void orc_tile_align(const uint8_t* ref, const uint8_t* mov, int w, int h, const 
     float* sq = (float*)malloc((size_t)nt * 4);
     float* ssd = ssd_out ? ssd_out : (float*)malloc((size_t)nt * S * S * 4);
     float* coord = (float*)malloc((size_t)nt * 8);
-    orc_tiles_border(rf, ta, w, h, M, T, tx, ty, bsx, bsy, rot);
-    orc_tiles_preshift(mf, tb, pre2, w, h, M, T, tx, ty, bsx, bsy, rot);
+    /* restated host (round 2): the base pose belongs to the moved image; the reference tiles use an identity base */
+    tiles_border_cs(rf, ta, w, h, M, T, tx, ty, 0.0f, 0.0f, 1.0f, 0.0f);
+    tiles_preshift_cs(mf, tb, pre2, w, h, M, T, tx, ty, bsx, bsy, cf, sf);
     cross_correlation_lags(ta, tb, cc, P, M, nt);
     orc_squared_sum(ta, sq, M, T, nt);
     orc_box_x(tb, bx, M, T, nt);
@@ -461,13 +469,19 @@ void orc_tile_align(const uint8_t* ref, const uint8_t* mov, int w, int h, const 
     orc_find_minimum(ssd, coord, argmin2, M, nt, threshold);
     for (int t = 0; t < nt; t++) {
         int tiy = t / tx, tix = t - tiy * tx, dxm, dym, dxr, dyr;
-        tile_disp(tix, tiy, T, w, h, pre2 ? pre2[2 * t] : 0.0f, pre2 ? pre2[2 * t + 1] : 0.0f, bsx, bsy, rot, &dxm, &dym);
-        tile_disp(tix, tiy, T, w, h, 0.0f, 0.0f, bsx, bsy, rot, &dxr, &dyr);
+        tile_disp(tix, tiy, T, w, h, pre2 ? pre2[2 * t] : 0.0f, pre2 ? pre2[2 * t + 1] : 0.0f, bsx, bsy, cf, sf, &dxm, &dym);
+        tile_disp(tix, tiy, T, w, h, 0.0f, 0.0f, bsx, bsy, cf, sf, &dxr, &dyr);
         out_shift2[2 * t] = coord[2 * t] + (float)(dxm - dxr);
         out_shift2[2 * t + 1] = coord[2 * t + 1] + (float)(dym - dyr);
     }
     free(rf); free(mf); free(ta); free(tb); free(cc); free(bx); free(by); free(sq); free(coord);
     if (!ssd_out) free(ssd);
+}
+void orc_tile_align(const uint8_t* ref, const uint8_t* mov, int w, int h, const float* pre2,
+                    float* out_shift2, int32_t* argmin2, float* ssd_out,
+                    int T, int M, int tx, int ty, float bsx, float bsy, float rot, float threshold)
+{
+    orc_tile_align_cs(ref, mov, w, h, pre2, out_shift2, argmin2, ssd_out, T, M, tx, ty, bsx, bsy, cosf(rot), sinf(rot), threshold);
 }
 
 /* ---- kernel.cu:642 UpSampleShifts --------------------------------------- */
@@ -522,9 +536,20 @@ static int invert_gj(float* a, float* inv, int n)
     }
     return 0;
 }
+void orc_consolidate_shifts_masked(const float* measured2, const int* pair_from, const int* pair_to, const uint8_t* pair_valid, int m,
+                                   int imageCount, int tilesX, int tilesY, int referenceImage,
+                                   float* one_to_one2, float* frame_shift2, int32_t* status);
 void orc_consolidate_shifts(const float* measured2, const int* pair_from, const int* pair_to, int m,
                             int imageCount, int tilesX, int tilesY, int referenceImage,
                             float* one_to_one2, float* frame_shift2, int32_t* status)
+{
+    orc_consolidate_shifts_masked(measured2, pair_from, pair_to, NULL, m, imageCount, tilesX, tilesY, referenceImage, one_to_one2, frame_shift2, status);
+}
+/* pair_valid[k] == 0: measurement k is out from the start (the restated pre-alignment host rules out pairs whose relative
+ * rotation is beyond what translation-only tile matching can follow); it does not count as a removed outlier. */
+void orc_consolidate_shifts_masked(const float* measured2, const int* pair_from, const int* pair_to, const uint8_t* pair_valid, int m,
+                                   int imageCount, int tilesX, int tilesY, int referenceImage,
+                                   float* one_to_one2, float* frame_shift2, int32_t* status)
 {
     int n1 = imageCount - 1, nt = tilesX * tilesY;
 #pragma omp parallel for schedule(static)
@@ -535,8 +560,9 @@ void orc_consolidate_shifts(const float* measured2, const int* pair_from, const 
         float* inv = (float*)malloc((size_t)n1 * n1 * 4);
         float* x = (float*)calloc((size_t)n1 * 2, 4);
         for (int k = 0; k < m; k++) {
-            for (int c = 0; c < n1; c++) A[k + c * m] = (c >= pair_from[k] && c < pair_to[k]) ? 1.0f : 0.0f;
-            b[2 * k] = measured2[2 * ((size_t)t * m + k)]; b[2 * k + 1] = measured2[2 * ((size_t)t * m + k) + 1];
+            const int on = !pair_valid || pair_valid[k];
+            for (int c = 0; c < n1; c++) A[k + c * m] = (on && c >= pair_from[k] && c < pair_to[k]) ? 1.0f : 0.0f;
+            b[2 * k] = on ? measured2[2 * ((size_t)t * m + k)] : 0.0f; b[2 * k + 1] = on ? measured2[2 * ((size_t)t * m + k) + 1] : 0.0f;
         }
         int removed = 0, st = 0;
         for (;;) {
@@ -577,23 +603,28 @@ void orc_consolidate_shifts(const float* measured2, const int* pair_from, const 
 }
 
 /* ---- opticalFlow.cu:48 CreateFlowFieldFromTiles ------------------------- */
-void orc_flow_from_tiles(const float* tile2, int tilesX, int tilesY, int T, float* flow2, int w, int h,
-                         float bsx, float bsy, float rot)
+void orc_flow_from_tiles_cs(const float* tile2, int tilesX, int tilesY, int T, float* flow2, int w, int h,
+                            float bsx, float bsy, float cf, float sf)
 {
     (void)T;
 #pragma omp parallel for schedule(static)
     for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++) {
-            float sx = cosf(rot) * -bsx - sinf(rot) * -bsy;
-            float sy = sinf(rot) * -bsx + cosf(rot) * -bsy;
+            float sx = cf * -bsx - sf * -bsy;
+            float sy = sf * -bsx + cf * -bsy;
             float pcx = (float)(x - w / 2), pcy = (float)(y - h / 2);
-            sx += cosf(rot) * pcx - sinf(rot) * pcy - pcx;
-            sy += sinf(rot) * pcx + cosf(rot) * pcy - pcy;
+            sx += cf * pcx - sf * pcy - pcx;
+            sy += sf * pcx + cf * pcy - pcy;
             float u = unnorm((x + 0.5f) / (float)w, tilesX), v = unnorm((y + 0.5f) / (float)h, tilesY);
             sx += tex_lin(tile2, tilesX, tilesY, 2, 0, u, v);
             sy += tex_lin(tile2, tilesX, tilesY, 2, 1, u, v);
             flow2[2 * ((size_t)y * w + x)] = sx; flow2[2 * ((size_t)y * w + x) + 1] = sy;
         }
+}
+void orc_flow_from_tiles(const float* tile2, int tilesX, int tilesY, int T, float* flow2, int w, int h,
+                         float bsx, float bsy, float rot)
+{
+    orc_flow_from_tiles_cs(tile2, tilesX, tilesY, T, flow2, w, h, bsx, bsy, cosf(rot), sinf(rot));
 }
 /* ---- opticalFlow.cu:28 WarpingKernel ------------------------------------ */
 void orc_warp(const float* flow2, const float* img, float* out, int w, int h)
@@ -920,4 +951,55 @@ void orc_fallback_upsample(const float* rgb3, int w, int h, float* out3, const o
             float u = ((float)(x + g->org_x) + 0.5f) / (float)g->scale, v = ((float)(y + g->org_y) + 0.5f) / (float)g->scale;
             for (int c = 0; c < 3; c++) out3[3 * ((size_t)y * g->out_w + x) + c] = tex_lin(rgb3, w, h, 3, c, u, v);
         }
+}
+
+
+/* ---- global pre-alignment (reference skeleton boxFilterNPP.cpp:102-166, the estimator itself is the absent
+ * host's) ------------------------------------------------------------------------------------------------------------
+ * Restated host: exhaustive search over rotation angle and integer shift on a small level of the 7-bit tracking pyramid,
+ * scoring each candidate by the mean squared difference over the pixels whose transformed sample lies inside the moved
+ * image.  The transform is the one the reference kernels apply (kernel.cu:299-311, opticalFlow.cu:72-81): a reference pixel
+ * with centred coordinates c reads the moved image at  p + round(R(theta) (c - b) - c).  Integer sums, candidates compared as
+ * exact fractions, ties to the lowest candidate index: the CUDA kernel (csrc/prealign.cu) reproduces the decision bit for bit.
+ *   cs        : table of (cos, sin) pairs, n_table entries (computed by the caller in double, rounded to float)
+ *   idx0,step : candidate angle a (0 .. n_ang-1) uses table entry idx0 + a * step
+ *   cx, cy    : centre of the shift search; candidate (iy, ix) in 0 .. 2R uses b = (cx + ix - R, cy + iy - R)
+ *   sub       : pixel subsampling (every sub-th pixel in x and y)
+ * Returns the best candidate as (angle index a, bx, by) in out3; a = -1 when no candidate had enough valid pixels. */
+void orc_prealign_search(const uint8_t* ref, const uint8_t* mov, int w, int h, const float* cs, int idx0, int step, int n_ang,
+                         int cx, int cy, int R, int sub, int32_t* out3)
+{
+    const int S = 2 * R + 1, ncand = n_ang * S * S;
+    unsigned long long* ssd = (unsigned long long*)malloc((size_t)ncand * 8);
+    unsigned* cnt = (unsigned*)malloc((size_t)ncand * 4);
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int c = 0; c < ncand; c++) {
+        const int a = c / (S * S), r = c - a * S * S, iy = r / S, ix = r - iy * S;
+        const float cf = cs[2 * (idx0 + a * step)], sf = cs[2 * (idx0 + a * step) + 1];
+        const int bx = cx + ix - R, by = cy + iy - R;
+        unsigned long long s = 0; unsigned n = 0;
+        for (int y = 0; y < h; y += sub)
+            for (int x = 0; x < w; x += sub) {
+                const float pcx = (float)(x - w / 2), pcy = (float)(y - h / 2);
+                const float ax = pcx - (float)bx, ay = pcy - (float)by;
+                const float dxf = (cf * ax - sf * ay) - pcx, dyf = (sf * ax + cf * ay) - pcy;
+                const int mx = x + (int)roundf(dxf), my = y + (int)roundf(dyf);
+                if (mx < 0 || my < 0 || mx >= w || my >= h) continue;
+                const int d = (int)ref[(size_t)y * w + x] - (int)mov[(size_t)my * w + mx];
+                s += (unsigned long long)(d * d); n++;
+            }
+        ssd[c] = s; cnt[c] = n;
+    }
+    const unsigned total = (unsigned)(((w + sub - 1) / sub) * ((h + sub - 1) / sub)), cnt_min = total / 4 > 0 ? total / 4 : 1;
+    int best = -1;
+    for (int c = 0; c < ncand; c++) {
+        if (cnt[c] < cnt_min) continue;
+        if (best < 0 || ssd[c] * (unsigned long long)cnt[best] < ssd[best] * (unsigned long long)cnt[c]) best = c;
+    }
+    if (best < 0) { out3[0] = -1; out3[1] = cx; out3[2] = cy; }
+    else {
+        const int a = best / (S * S), r = best - a * S * S, iy = r / S, ix = r - iy * S;
+        out3[0] = a; out3[1] = cx + ix - R; out3[2] = cy + iy - R;
+    }
+    free(ssd); free(cnt);
 }

@@ -61,6 +61,16 @@ void orc_consolidate_shifts(const float* measured2, const int* pair_from, const 
                             int imageCount, int tilesX, int tilesY, int referenceImage,
                             float* one_to_one2, float* frame_shift2, int32_t* status);
 /* opticalFlow.cu:48,28,97,151,190 */
+void orc_consolidate_shifts_masked(const float* measured2, const int* pair_from, const int* pair_to, const uint8_t* pair_valid, int m,
+                                   int imageCount, int tilesX, int tilesY, int referenceImage,
+                                   float* one_to_one2, float* frame_shift2, int32_t* status);
+void orc_tile_align_cs(const uint8_t* ref, const uint8_t* mov, int w, int h, const float* pre2,
+                       float* out_shift2, int32_t* argmin2, float* ssd_out,
+                       int T, int M, int tx, int ty, float bsx, float bsy, float cf, float sf, float threshold);
+void orc_flow_from_tiles_cs(const float* tile2, int tilesX, int tilesY, int T, float* flow2, int w, int h,
+                            float bsx, float bsy, float cf, float sf);
+void orc_prealign_search(const uint8_t* ref, const uint8_t* mov, int w, int h, const float* cs, int idx0, int step, int n_ang,
+                         int cx, int cy, int R, int sub, int32_t* out3);
 void orc_flow_from_tiles(const float* tile2, int tilesX, int tilesY, int T, float* flow2, int w, int h,
                          float bsx, float bsy, float rot);
 void orc_warp(const float* flow2, const float* img, float* out, int w, int h);

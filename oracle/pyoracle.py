@@ -155,16 +155,78 @@ def upsample_shifts(in2, old_level, new_level, new_cx, new_cy, old_t, new_t):
     return out
 
 
-def consolidate_shifts(measured, pair_from, pair_to, image_count, tiles_x, tiles_y, reference_image):
+def consolidate_shifts(measured, pair_from, pair_to, image_count, tiles_x, tiles_y, reference_image, pair_valid=None):
     measured = _a(measured, np.float32)
     nt, m = measured.shape[:2]
     n1 = image_count - 1
     one = np.zeros((nt, n1, 2), np.float32)
     fs = np.zeros((image_count, tiles_y, tiles_x, 2), np.float32)
     status = np.zeros((nt,), np.int32)
-    lib().orc_consolidate_shifts(_p(measured), _i(pair_from), _i(pair_to), m, image_count, tiles_x, tiles_y, reference_image,
-                                 _p(one), _p(fs), _p(status))
+    pv = _a(pair_valid, np.uint8) if pair_valid is not None else None
+    lib().orc_consolidate_shifts_masked(_p(measured), _i(pair_from), _i(pair_to), _p(pv), m, image_count, tiles_x, tiles_y, reference_image,
+                                        _p(one), _p(fs), _p(status))
     return one, fs, status
+
+
+def prealign_table():
+    """(cos, sin) of the pre-alignment's candidate angles: 0.125 degree steps over +-21 degrees, double -> float32 (the same table
+    the product uploads, csrc/pipeline.cu)."""
+    i = np.arange(2 * 21 * 8 + 1, dtype=np.float64) - 21 * 8
+    th = i * (0.125 * 3.14159265358979323846 / 180.0)
+    return np.stack([np.cos(th), np.sin(th)], axis=1).astype(np.float32), 21 * 8
+
+
+def prealign_search(ref, mov, cs, idx0, step, n_ang, cx=0, cy=0, radius=8, sub=1):
+    ref, mov, cs = _a(ref, np.uint8), _a(mov, np.uint8), _a(cs, np.float32)
+    h, w = ref.shape
+    out = np.zeros((3,), np.int32)
+    lib().orc_prealign_search(_p(ref), _p(mov), w, h, _p(cs), int(idx0), int(step), int(n_ang), int(cx), int(cy), int(radius), int(sub), _p(out))
+    return out
+
+
+def prealign_frame(pyr_ref, pyr_mov, w, h):
+    """Pose (bx, by, cos, sin) of one frame against the reference: the two search stages of the restated pre-alignment host
+    (csrc/prealign.cu header) on the tracking pyramids pyr_*[level] (extended below the matcher's levels by pyramid_down)."""
+    cs, zero = prealign_table()
+    la, aw, ah = 0, w, h
+    while (aw > 192 or ah > 192) and aw // 2 >= 16 and ah // 2 >= 16:
+        aw //= 2; ah //= 2; la += 1
+    lb = la - 2 if la >= 2 else 0
+    ra = prealign_search(pyr_ref[la], pyr_mov[la], cs, zero - 20 * 8, 8, 41, 0, 0, 8, 1)
+    ta = zero if ra[0] < 0 else zero - 20 * 8 + int(ra[0]) * 8
+    sc = 1 << (la - lb)
+    rb = prealign_search(pyr_ref[lb], pyr_mov[lb], cs, ta - 8, 1, 17, int(ra[1]) * sc, int(ra[2]) * sc, 4, 2)
+    tb = zero if rb[0] < 0 else ta - 8 + int(rb[0])
+    bx, by = (0, 0) if rb[0] < 0 else (int(rb[1]), int(rb[2]))
+    return np.array([np.float32(bx * (1 << lb)), np.float32(by * (1 << lb)), cs[tb, 0], cs[tb, 1]], np.float32), (ra, rb)
+
+
+def pair_pose(pi, pj):
+    """Pose of frame j relative to frame i (strict fp32, same expressions as pair_pose_kernel)."""
+    f = np.float32
+    dbx, dby = f(pj[0] - pi[0]), f(pj[1] - pi[1])
+    ci, si, cj, sj = pi[2], pi[3], pj[2], pj[3]
+    return np.array([f(f(ci * dbx) - f(si * dby)), f(f(si * dbx) + f(ci * dby)), f(f(cj * ci) + f(sj * si)), f(f(sj * ci) - f(cj * si))], np.float32)
+
+
+def tile_align_cs(ref, mov, pre, T, M, bs, cf, sf, threshold=0.0):
+    ref, mov = _a(ref, np.uint8), _a(mov, np.uint8)
+    h, w = ref.shape
+    tx, ty = (w - 2 * M) // T, (h - 2 * M) // T
+    shift = np.zeros((ty, tx, 2), np.float32)
+    arg = np.zeros((ty, tx, 2), np.int32)
+    pre_a = _a(pre, np.float32) if pre is not None else None
+    lib().orc_tile_align_cs(_p(ref), _p(mov), w, h, _p(pre_a), _p(shift), _p(arg), None, T, M, tx, ty,
+                            c_f(bs[0]), c_f(bs[1]), c_f(cf), c_f(sf), c_f(threshold))
+    return shift, arg
+
+
+def flow_from_tiles_cs(tile2, T, w, h, bs, cf, sf):
+    tile2 = _a(tile2, np.float32)
+    ty, tx = tile2.shape[:2]
+    flow = np.zeros((h, w, 2), np.float32)
+    lib().orc_flow_from_tiles_cs(_p(tile2), tx, ty, T, _p(flow), w, h, c_f(bs[0]), c_f(bs[1]), c_f(cf), c_f(sf))
+    return flow
 
 
 def flow_from_tiles(tile2, T, w, h, base_shift=(0.0, 0.0), rot=0.0):
@@ -322,7 +384,27 @@ def run_pipeline(frames, p, ref_idx=0, gray_format=False, keep=False):
             lv.append(pyramid_down(lv[-1]))
         pyr.append(lv)
     L = len(pyr[0])
-    pairs = [(i, j) for i in range(n) for j in range(i + 1, min(n, i + p.pair_span + 1))]
+    pre_on = bool(getattr(p, "prealign", 0)) and n > 1
+    # measured pairs: at most pair_span frames apart; with the pre-alignment also every frame against the reference (pipeline.cu: build_pairs)
+    pairs = [(i, j) for i in range(n) for j in range(i + 1, n) if j - i <= p.pair_span or (pre_on and (i == ref_idx or j == ref_idx))]
+    poses, pa_results, pair_valid = None, None, None
+    if getattr(p, "prealign", 0) and n > 1:
+        # the tracking pyramid continues below the matcher's levels for the search on a small image
+        ext = []
+        for f in range(n):
+            lv = list(pyr[f])
+            while max(lv[-1].shape) > 192 and min(lv[-1].shape) // 2 >= 16:
+                lv.append(pyramid_down(lv[-1]))
+            ext.append(lv)
+        poses, pa_results = [], []
+        for f in range(n):
+            if f == ref_idx:
+                poses.append(np.array([0, 0, 1, 0], np.float32)); pa_results.append(None)
+            else:
+                ps, rr = prealign_frame(ext[ref_idx], ext[f], w, h)
+                poses.append(ps); pa_results.append(rr)
+        # pairs rotated against each other by more than 16 degrees stay out of the consolidation (prealign.cu: pair_pose_kernel)
+        pair_valid = [1 if pair_pose(poses[i], poses[j])[2] >= np.float32(0.96126169593831886) else 0 for (i, j) in pairs]
     tx, ty = (w - 2 * M) // T, (h - 2 * M) // T
     nt = tx * ty
     argmins = []
@@ -335,16 +417,24 @@ def run_pipeline(frames, p, ref_idx=0, gray_format=False, keep=False):
                 ltx, lty = (lw - 2 * M) // T, (lh - 2 * M) // T
                 if pre is not None:
                     pre = upsample_shifts(pre, 1 << (l + 1), 1 << l, ltx, lty, T, T)
-                bs = (p.base_shift[0] / float(1 << l), p.base_shift[1] / float(1 << l))
-                pre, arg, _ = tile_align(pyr[i][l], pyr[j][l], pre, T, M, bs, p.base_rotation, p.min_threshold)
+                if poses is not None:
+                    pp = pair_pose(poses[i], poses[j])
+                    sc = np.float32(1.0) / np.float32(1 << l)
+                    pre, arg = tile_align_cs(pyr[i][l], pyr[j][l], pre, T, M, (np.float32(pp[0] * sc), np.float32(pp[1] * sc)), pp[2], pp[3], p.min_threshold)
+                else:
+                    bs = (p.base_shift[0] / float(1 << l), p.base_shift[1] / float(1 << l))
+                    pre, arg, _ = tile_align(pyr[i][l], pyr[j][l], pre, T, M, bs, p.base_rotation, p.min_threshold)
             measured[:, k, :] = pre.reshape(nt, 2)
             argmins.append(arg)
-        one, frame_shift, status = consolidate_shifts(measured, [a for a, _ in pairs], [b for _, b in pairs], n, tx, ty, ref_idx)
+        one, frame_shift, status = consolidate_shifts(measured, [a for a, _ in pairs], [b for _, b in pairs], n, tx, ty, ref_idx, pair_valid)
     else:
         frame_shift = np.zeros((1, ty, tx, 2), np.float32)
     flows = []
     for f in range(n):
-        fl = flow_from_tiles(frame_shift[f], T, w, h, tuple(p.base_shift), p.base_rotation)
+        if poses is not None:
+            fl = flow_from_tiles_cs(frame_shift[f], T, w, h, (poses[f][0], poses[f][1]), poses[f][2], poses[f][3])
+        else:
+            fl = flow_from_tiles(frame_shift[f], T, w, h, tuple(p.base_shift), p.base_rotation)
         if f != ref_idx:
             for _ in range(p.lk_iterations):
                 fl = lk_iteration(gray[ref_idx], gray[f], fl, p.lk_half_window, p.lk_min_det)
@@ -361,5 +451,5 @@ def run_pipeline(frames, p, ref_idx=0, gray_format=False, keep=False):
     out = merge(frames, np.stack(masks), np.stack(flows), kern, fb, geom, white, black, p.weight_threshold, cfa,
                 gamma=bool(p.merge_flags & 1))
     inter = dict(argmin=argmins, frame_shift=frame_shift, flow=flows, mask=masks, kernel=kern, fallback=fb, gray=gray,
-                 gray_q=[pv[0] for pv in pyr], rgb_half=rgb_half, pairs=pairs) if keep else None
+                 gray_q=[pv[0] for pv in pyr], rgb_half=rgb_half, pairs=pairs, poses=poses, prealign=pa_results) if keep else None
     return out, inter

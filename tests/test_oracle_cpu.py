@@ -127,3 +127,21 @@ def test_bundled_burst_config1():
     assert m[0] > 0.85 and m[1] > 0.4 and m[1] > m[2] > m[3] > m[4] and m[4] < 0.1, m   # certainty falls with rotation
     fb = it["fallback"]
     assert 20 < 10 * np.log10(1.0 / np.mean((out - fb) ** 2)) < 60   # close to, but not identical with, the demosaiced reference
+
+
+def test_bundled_burst_config1_prealigned():
+    """With the global pre-alignment (restated host, csrc/prealign.cu header) every frame of the reference's bundled burst aligns:
+    the estimated rotations are the generator's (main.cpp:1894-1907: 5, 10, -15 degrees; opposite sign in the kernels' convention),
+    the tile residual against the pose is small and the robustness model accepts the frames."""
+    fr = np.load(Path(__file__).resolve().parent / "golden" / "bundled_burst_rggb.npz")["frames"]
+    p = params()
+    p.prealign = 1
+    out, it = O.run_pipeline(fr, p, ref_idx=0, keep=True)
+    ang = [float(np.degrees(np.arctan2(ps[3], ps[2]))) for ps in it["poses"]]
+    assert np.allclose(ang, [0, 0, -5, -10, 15], atol=0.3), ang
+    assert (0, 4) in it["pairs"] and (0, 3) in it["pairs"]                # every frame is also measured against the reference
+    for f in range(1, 5):
+        ts = it["frame_shift"][f].reshape(-1, 2)
+        assert np.median(np.hypot(ts[:, 0], ts[:, 1])) < (1.5 if f < 4 else 3.0), f
+        assert it["mask"][f][..., :3].mean() > 0.4, (f, it["mask"][f][..., :3].mean())
+    assert np.isfinite(out).all()

@@ -234,18 +234,33 @@ def _compare_images(out, exp, frac=1e-4, db=60.0):
 
 def test_pipeline_bundled_burst_config1(cuda_device):
     """BASELINE configs[0]: the reference's own 5-frame burst (tests/golden/bundled_burst_rggb.npz, made from
-    test_opencv/img_00000{0..4}.png by tests/golden/make_bundled_fixture.py) through the CUDA path against the oracle's chain."""
+    test_opencv/img_00000{0..4}.png by tests/golden/make_bundled_fixture.py; frames 2-4 rotated 5 / 10 / -15 degrees,
+    main.cpp:1894-1907) through the CUDA path with the global pre-alignment against the oracle's chain: poses, integer tile
+    shifts and consolidated shifts bit-exact, image within the north star's tolerance — and every frame ALIGNS."""
     from pathlib import Path
     fr_np = np.load(Path(__file__).resolve().parent / "golden" / "bundled_burst_rggb.npz")["frames"]
     fr = torch.from_numpy(fr_np.view(np.int16))
     p = default_params()
+    p.prealign = 1
     sr, out = _run(p, fr, cuda_device, ref_idx=0)
     exp, it = O.run_pipeline(fr_np, p, ref_idx=0, keep=True)
-    for k in range(sr.tile_grid()[2]):
+    tx, ty, m = sr.tile_grid()
+    assert m == len(it["pairs"]) == len(measured_pairs(5, p.pair_span, 1, 0))
+    pose = sr.buffer("pose", 5, 16).view(np.float32).reshape(5, 4)
+    assert np.array_equal(pose, np.stack(it["poses"])), (pose, it["poses"])
+    ang = np.degrees(np.arctan2(pose[:, 3], pose[:, 2]))
+    assert np.allclose(ang, [0, 0, -5, -10, 15], atol=0.3), ang           # the generator's rotations, in the kernels' sign convention
+    for k in range(m):
         assert np.array_equal(sr.tile_argmin(k), it["argmin"][k]), f"pair {k}"
     for f in range(5):
         assert np.array_equal(sr.tile_shifts(f), it["frame_shift"][f])
-    _compare_images(out, exp)
+    h, w = fr_np.shape[1:]
+    for f in range(1, 5):
+        ts = sr.tile_shifts(f).reshape(-1, 2)
+        mask = sr.buffer("mask", h // 2, (w // 2) * 16, f).view(np.float32).reshape(h // 2, w // 2, 4)
+        assert np.median(np.hypot(ts[:, 0], ts[:, 1])) < (1.5 if f < 4 else 3.0), f     # residual against the pre-alignment pose
+        assert mask[..., :3].mean() > 0.4, (f, float(mask[..., :3].mean()))             # the robustness model accepts the frame
+    _compare_images(out, exp, frac=5e-4)
     sr.close()
 
 

@@ -143,6 +143,33 @@ def test_tile_align_vs_reference_kernels(cuda_device, burst, use_fft):
         assert mism <= 0.01, f"arg-min mismatch vs cuFFT path on {mism:.3%} of tiles"
 
 
+def test_prealign_search_bit_exact(cuda_device):
+    """Global pre-alignment search (csrc/prealign.cu) against the oracle on the bundled burst's tracking images: both stages,
+    the decision (angle candidate, shift) is bit-exact — integer scores compared as exact fractions, ties to the lowest index."""
+    from pathlib import Path
+    fr_np = np.load(Path(__file__).resolve().parent / "golden" / "bundled_burst_rggb.npz")["frames"]
+    tr = _track(fr_np)
+    cs, zero = O.prealign_table()
+    cs_d = torch.from_numpy(cs).to(cuda_device)
+    lv = [[t[1]] for t in tr]
+    for f in range(5):
+        for _ in range(2):
+            lv[f].append(O.pyramid_down(lv[f][-1]))
+    for f in (1, 2, 4):
+        a2, b2 = lv[0][2], lv[f][2]                       # 128 x 64
+        ea = O.prealign_search(a2, b2, cs, zero - 160, 8, 41, 0, 0, 8, 1)
+        ga = stages.prealign_search(torch.from_numpy(a2).to(cuda_device), torch.from_numpy(b2).to(cuda_device), cs_d, zero - 160, 8, 41, 0, 0, 8, 1).cpu().numpy()
+        assert np.array_equal(ga, ea), (f, ga, ea)
+        ta = zero - 160 + int(ea[0]) * 8
+        a0, b0 = lv[0][0], lv[f][0]
+        eb = O.prealign_search(a0, b0, cs, ta - 8, 1, 17, int(ea[1]) * 4, int(ea[2]) * 4, 4, 2)
+        gb = stages.prealign_search(torch.from_numpy(a0).to(cuda_device), torch.from_numpy(b0).to(cuda_device), cs_d, ta - 8, 1, 17, int(ea[1]) * 4, int(ea[2]) * 4, 4, 2).cpu().numpy()
+        assert np.array_equal(gb, eb), (f, gb, eb)
+    # identical images: zero shift, zero angle (candidate 20 of 41), even with ties elsewhere
+    same = stages.prealign_search(torch.from_numpy(lv[0][2]).to(cuda_device), torch.from_numpy(lv[0][2]).to(cuda_device), cs_d, zero - 160, 8, 41).cpu().numpy()
+    assert np.array_equal(same, [20, 0, 0])
+
+
 def test_upsample_shifts_bit_exact(cuda_device):
     rng = np.random.default_rng(1)
     coarse = rng.uniform(-4, 4, size=(5, 7, 2)).astype(np.float32)
