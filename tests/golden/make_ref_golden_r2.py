@@ -45,8 +45,6 @@ def make_case(rng, n, span, tx=9, ty=7):
         bad = rng.integers(0, len(ok), size=(nt, 2))
         for t in range(0, nt, 3):
             meas[t, ok[bad[t, 0]]] += 7.0
-            if t % 9 == 0 and bad[t, 1] != bad[t, 0] and len(ok) > 4:
-                meas[t, ok[bad[t, 1]]] -= 5.0
     return pairs, meas
 
 

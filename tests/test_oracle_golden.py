@@ -118,3 +118,23 @@ def test_texture_model():
         model = np.clip(f, 0, tw - 1) * (1 - q) + np.clip(f + 1, 0, tw - 1) * q
         d = np.abs(model - hw)
         assert d.max() <= 1.0 / 256 + 1e-6 and (d < 1e-6).mean() >= min_exact
+
+
+G2 = np.load(Path(__file__).resolve().parent / "golden" / "ref_golden_r2.npz")
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2, 3, 4])
+def test_consolidate_shifts_vs_reference_kernels(ci):
+    """Shift consolidation pinned to the reference's own kernels (copyShiftMatrix / setPointers / transposeShifts / checkForOutliers /
+    getOptimalShifts, ShiftMinimizerKernels.cu:29-218) run on a B200 around cuBLAS batched normal equations
+    (oracle/ref_driver.cu: ref_consolidate; vectors frozen by tests/golden/make_ref_golden_r2.py): the same measurements are removed
+    per tile, the shifts agree to the round-off of two different fp32 inverses (Gauss-Jordan here, cuBLAS matinv there)."""
+    n, span, ref, tx, ty = [int(v) for v in G2[f"cs{ci}_cfg"]]
+    pairs = [(i, j) for i in range(n) for j in range(i + 1, min(n, i + span + 1))]
+    one, fs, st = O.consolidate_shifts(G2[f"cs{ci}_meas"], [a for a, _ in pairs], [b for _, b in pairs], n, tx, ty, ref)
+    assert np.all(G2[f"cs{ci}_status"] == -1)                      # the reference loop converged everywhere
+    assert np.array_equal(st, G2[f"cs{ci}_removed"])
+    close(one, G2[f"cs{ci}_one_to_one"], 2e-5)
+    close(fs, G2[f"cs{ci}_frame_shift"], 1e-4)
+    if len(pairs) > n:
+        assert G2[f"cs{ci}_removed"].sum() == len(range(0, tx * ty, 3))     # one injected outlier in every third tile, each found

@@ -260,7 +260,11 @@ def test_pipeline_bundled_burst_config1(cuda_device):
         mask = sr.buffer("mask", h // 2, (w // 2) * 16, f).view(np.float32).reshape(h // 2, w // 2, 4)
         assert np.median(np.hypot(ts[:, 0], ts[:, 1])) < (1.5 if f < 4 else 3.0), f     # residual against the pre-alignment pose
         assert mask[..., :3].mean() > 0.4, (f, float(mask[..., :3].mean()))             # the robustness model accepts the frame
-    _compare_images(out, exp, frac=5e-4)
+    # The photograph has flat and saturated regions where lucasKanadeOptim's 2x2 system is singular (opticalFlow.cu:232-262: the
+    # minDet branch and the pseudo-inverse of a rank-deficient matrix): there the refined flow is decided by round-off, CUDA (MUFU
+    # sqrt / rcp) and the oracle (libm) land on different sides of round(2 * flow) for ~1 % of the pixels, and 0.2 % of the image
+    # samples move by more than 1e-3 (tools/bundled_debug.py).  Synthetic bursts, textured everywhere, stay below 1e-5.
+    _compare_images(out, exp, frac=3e-3, db=40.0)
     sr.close()
 
 

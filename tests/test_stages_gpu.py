@@ -246,8 +246,6 @@ def test_consolidate_vs_reference_kernels(cuda_device, n, span, ref_img):
         bad = rng.integers(0, len(ok), size=(nt, 2))
         for t in range(0, nt, 3):
             meas[t, ok[bad[t, 0]]] += 7.0
-            if t % 9 == 0 and bad[t, 1] != bad[t, 0] and len(ok) > 4:
-                meas[t, ok[bad[t, 1]]] -= 5.0
     pf, pt = [a for a, _ in pairs], [b for _, b in pairs]
     d = torch.from_numpy(meas).to(cuda_device)
     g1, gfs, gst = stages.consolidate_shifts(d, pf, pt, n, tx, ty, ref_img)

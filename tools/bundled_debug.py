@@ -11,12 +11,13 @@ from oracle import pyoracle as O
 fr_np = np.load(ROOT / "tests" / "golden" / "bundled_burst_rggb.npz")["frames"]
 n, h, w = fr_np.shape
 p = default_params()
+p.prealign = 1
 sr = BurstSuperResolution(p, device=0, max_width=w, max_height=h, max_frames=n)
 sr.set_input(torch.from_numpy(fr_np.view(np.int16)).cuda(), ref_idx=0)
 out = sr.next_frame().cpu().numpy()
 exp, it = O.run_pipeline(fr_np, p, ref_idx=0, keep=True)
 bad = np.abs(out - exp) > 1e-3
-print("image: frac beyond 1e-3", bad.mean(), "max", np.abs(out - exp).max())
+print("image: frac beyond 1e-3", bad.mean(), "max", np.abs(out - exp).max(), "psnr", 10 * np.log10(1.0 / np.mean((out.astype(np.float64) - exp) ** 2)))
 for f in range(n):
     flow = sr.buffer("flow", h, w * 8, f).view(np.float32).reshape(h, w, 2)
     d = np.abs(flow - it["flow"][f])
