@@ -240,6 +240,12 @@ int mfsr_stage_lk_iteration(const float* ref, const float* mov, int64_t img_pitc
                             const float* flow_in, float* flow_out, int64_t flow_pitch,
                             int width, int height, int half_window, float min_det,
                             void* stream);
+/* The same sweep with the bilinear fetch of the warp on the TEXTURE UNIT, as the reference's WarpingKernel does it
+ * (opticalFlow.cu:36-41); `mov` must be 512-byte aligned with a pitch that is a multiple of 32 bytes. */
+int mfsr_stage_lk_iteration_tex(const float* ref, const float* mov, int64_t img_pitch,
+                            const float* flow_in, float* flow_out, int64_t flow_pitch,
+                            int width, int height, int half_window, float min_det,
+                            void* stream);
 
 /* ComputeDerivatives2Kernel -> ComputeStructureTensor -> (2r+1)^2 box mean
  * (clamp border) -> ComputeKernelParam, fused.  Output float4 (b22,b11,-b12,0)/det. */

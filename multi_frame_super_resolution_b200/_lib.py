@@ -81,6 +81,7 @@ SIGNATURES = {
     "mfsr_stage_consolidate_shifts": (c_i, [vp, ip, ip, c_i, c_i, c_i, c_i, c_i, vp, vp, vp, vp]),
     "mfsr_stage_flow_from_tiles": (c_i, [vp, c_i64, c_i, c_i, c_i, vp, c_i64, c_i, c_i, c_f, c_f, c_f, vp]),
     "mfsr_stage_lk_iteration": (c_i, [vp, vp, c_i64, vp, vp, c_i64, c_i, c_i, c_i, c_f, vp]),
+    "mfsr_stage_lk_iteration_tex": (c_i, [vp, vp, c_i64, vp, vp, c_i64, c_i, c_i, c_i, c_f, vp]),
     "mfsr_stage_kernel_params": (c_i, [vp, c_i64, vp, c_i64, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f, vp]),
     "mfsr_stage_robustness": (c_i, [vp, vp, c_i64, vp, c_i64, vp, c_i64, vp, c_i, c_i, c_f, c_f, c_f, c_i, vp]),
     "mfsr_stage_merge": (c_i, [vp, c_i64, c_i64, vp, c_i64, c_i64, vp, c_i64, c_i64, vp, c_i64, vp, c_i64,

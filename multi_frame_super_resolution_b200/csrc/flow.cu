@@ -98,12 +98,18 @@ __device__ __forceinline__ bool lk_pinv(float a, float b, float c, float d, floa
 // loop below is a compile-time constant: the first version (runtime hw, per-element clamped stencils, one output per
 // thread in the window sums) executed 1170 instructions per pixel at 82 % issue utilisation (profiles/r1j_lk_ncu.txt).
 //   W region (source + warped): tile + HW + 2 on each side      R region (derivatives): tile + HW
-template <int HW, bool BAND>
+// MODE 0: the bilinear fetch of the warp step is evaluated in ALU with the 1.8 fixed-point texture model of common.cuh (bit-identical
+//         to the oracle's restatement); MODE 1: the same for a row band (texture rows of the FULL frame);
+// MODE 2: the fetch goes through the texture unit, exactly as the reference's WarpingKernel does it (opticalFlow.cu:36-41: linear
+//         filter, clamp addressing, normalised coordinates) — one TEX instead of four loads and ~30 ALU instructions per element of
+//         the haloed region, and the warped image is the reference kernel's bit for bit.
+template <int HW, int MODE>
 __global__ void __launch_bounds__(256, 4)
 lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov, int64_t img_pitch,
                     const float2* __restrict__ flow_in, float2* __restrict__ flow_out, int64_t flow_pitch,
-                    int w, int h, float minDet, int gh, int gy0)
+                    int w, int h, float minDet, int gh, int gy0, cudaTextureObject_t movtex)
 {
+    constexpr bool BAND = MODE == 1;
     // gh / gy0: height of the full frame and global row of local row 0 (row-band mode; gh == h, gy0 == 0 otherwise): the warp's
     // texture coordinates are normalised by the FULL frame so that a band reproduces the full-frame arithmetic bit for bit
     constexpr int RW = LTW + 2 * HW, RH = LTH + 2 * HW;       // derivative region
@@ -146,6 +152,20 @@ lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov
                     if (ok[k]) { srcv[k] = __ldg(ref + (unsigned)(gy[k] * pe + gx)); fl[k] = __ldg(flow_in + (unsigned)(gy[k] * pf + gx)); }
                     else { srcv[k] = 0.f; fl[k] = make_float2(0.f, 0.f); }
                 }
+                if constexpr (MODE == 2) {
+                    float wv[CNT];
+#pragma unroll
+                    for (int k = 0; k < CNT; k++) {
+                        const float px = fgx + fl[k].x, py = (float)gy[k] + 0.5f + fl[k].y;
+                        float qx = px * rw, qy = py * rh;                    // correctly rounded px / w, py / h (see above)
+                        qx = __fmaf_rn(__fmaf_rn(-fw, qx, px), rw, qx);
+                        qy = __fmaf_rn(__fmaf_rn(-fh, qy, py), rh, qy);
+                        wv[k] = ok[k] ? tex2D<float>(movtex, qx, qy) : 0.f;
+                    }
+#pragma unroll
+                    for (int k = 0; k < CNT; k++)
+                        if (ok[k]) { s_src[ly[k]][lx] = srcv[k] + wv[k]; s_wrp[ly[k]][lx] = wv[k] - srcv[k]; }
+                } else {
                 float t00[CNT], t10[CNT], t01[CNT], t11[CNT], fa[CNT], fb[CNT];
 #pragma unroll
                 for (int k = 0; k < CNT; k++) {
@@ -173,6 +193,7 @@ lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov
                         s_src[ly[k]][lx] = srcv[k] + wv;
                         s_wrp[ly[k]][lx] = wv - srcv[k];
                     }
+                }
             };
             constexpr int WB = 4;
 #pragma unroll
@@ -302,7 +323,7 @@ extern "C" int mfsr_stage_flow_from_tiles(const float* tile_shift, int64_t tile_
 }
 
 int mfsr::launch_lk_iteration(const float* ref, const float* mov, int64_t img_pitch, const float2* flow_in, float2* flow_out, int64_t flow_pitch,
-                              int width, int height, int half_window, float min_det, int gh, int gy0, cudaStream_t st)
+                              int width, int height, int half_window, float min_det, int gh, int gy0, cudaStream_t st, cudaTextureObject_t movtex)
 {
     if (!ref || !mov || !flow_in || !flow_out || flow_in == flow_out || width < 1 || height < 1) return MFSR_E_INVALID;
     if (half_window < 1 || half_window > LHW_MAX) return MFSR_E_INVALID;
@@ -311,8 +332,10 @@ int mfsr::launch_lk_iteration(const float* ref, const float* mov, int64_t img_pi
     if (gh <= 0) { gh = height; gy0 = 0; }
     dim3 b(LTW, 8), g(cdiv(width, LTW), cdiv(height, LTH));
     const bool band = !(gh == height && gy0 == 0);
-#define MFSR_LK(HW_) do { if (band) lk_iteration_kernel<HW_, true><<<g, b, 0, st>>>(ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0); \
-                          else lk_iteration_kernel<HW_, false><<<g, b, 0, st>>>(ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0); } while (0)
+    if (band) movtex = 0;             // a band reproduces the full frame bit for bit only with the ALU model (texture rows of the full frame)
+#define MFSR_LK(HW_) do { if (band) lk_iteration_kernel<HW_, 1><<<g, b, 0, st>>>(ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0, 0); \
+                          else if (movtex) lk_iteration_kernel<HW_, 2><<<g, b, 0, st>>>(ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0, movtex); \
+                          else lk_iteration_kernel<HW_, 0><<<g, b, 0, st>>>(ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0, 0); } while (0)
     switch (half_window) {
         case 1: MFSR_LK(1); break;
         case 2: MFSR_LK(2); break;
@@ -324,9 +347,40 @@ int mfsr::launch_lk_iteration(const float* ref, const float* mov, int64_t img_pi
     return MFSR_OK;
 }
 
+// linear-filter / clamp / normalised-coordinate texture over a pitched float image (what the reference binds, opticalFlow.cu:36-41)
+int mfsr::make_gray_texture(const float* img, int64_t pitch, int width, int height, cudaTextureObject_t* out)
+{
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypePitch2D;
+    rd.res.pitch2D.devPtr = (void*)img; rd.res.pitch2D.desc = cudaCreateChannelDesc<float>();
+    rd.res.pitch2D.width = (size_t)width; rd.res.pitch2D.height = (size_t)height; rd.res.pitch2D.pitchInBytes = (size_t)pitch;
+    cudaTextureDesc td = {};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeElementType; td.normalizedCoords = 1;
+    MFSR_CUDA_TRY(cudaCreateTextureObject(out, &rd, &td, nullptr));
+    return MFSR_OK;
+}
+
 extern "C" int mfsr_stage_lk_iteration(const float* ref, const float* mov, int64_t img_pitch, const float* flow_in, float* flow_out,
                                        int64_t flow_pitch, int width, int height, int half_window, float min_det, void* stream)
 {
     return launch_lk_iteration(ref, mov, img_pitch, (const float2*)flow_in, (float2*)flow_out, flow_pitch, width, height, half_window, min_det,
-                               0, 0, (cudaStream_t)stream);
+                               0, 0, (cudaStream_t)stream, 0);
+}
+
+// The same sweep with the warp's bilinear fetch on the texture unit (what mfsr_run uses outside row-band mode).  `mov` must satisfy the
+// device's texture alignment (base 512 B, pitch 32 B).  The texture object lives for the duration of the call (the stream is
+// synchronised before it is destroyed): a test entry point, not a hot path.
+extern "C" int mfsr_stage_lk_iteration_tex(const float* ref, const float* mov, int64_t img_pitch, const float* flow_in, float* flow_out,
+                                           int64_t flow_pitch, int width, int height, int half_window, float min_det, void* stream)
+{
+    if (!mov || ((uintptr_t)mov & 511) || (img_pitch & 31)) return MFSR_E_INVALID;
+    cudaTextureObject_t t = 0;
+    int rc = make_gray_texture(mov, img_pitch, width, height, &t);
+    if (rc) return rc;
+    rc = launch_lk_iteration(ref, mov, img_pitch, (const float2*)flow_in, (float2*)flow_out, flow_pitch, width, height, half_window, min_det,
+                             0, 0, (cudaStream_t)stream, t);
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaDestroyTextureObject(t);
+    return rc;
 }

@@ -55,6 +55,8 @@ int launch_pair_pose(const float* pose, const PairTable& pt, int m, float* pair_
 
 // one Lucas-Kanade sweep; gh / gy0 as above (0: whole frame)
 int launch_lk_iteration(const float* ref, const float* mov, int64_t img_pitch, const float2* flow_in, float2* flow_out, int64_t flow_pitch,
-                        int width, int height, int half_window, float min_det, int gh, int gy0, cudaStream_t st);
+                        int width, int height, int half_window, float min_det, int gh, int gy0, cudaStream_t st, cudaTextureObject_t movtex = 0);
+// movtex != 0 (and not a band): the warp step samples the moved image through this texture (make_gray_texture) instead of the ALU model
+int make_gray_texture(const float* img, int64_t pitch, int width, int height, cudaTextureObject_t* out);
 
 }  // namespace mfsr

@@ -63,6 +63,8 @@ struct mfsr_context {
     float* pa_cs; char* pa_scratch; size_t pa_scratch_bytes;
     float* pose; float* pair_pose; int* pa_result;      // per frame (bx, by, cos, sin); per pair; per frame and stage (a, bx, by)
     unsigned long long* pair_valid;                     // bit k: pair k takes part in the shift consolidation
+    // linear-filter textures over the tracking gray frames (the LK warp step samples the moved frame through the texture unit)
+    cudaTextureObject_t gray_tex[CONS_MAX_N + 1]; int n_gray_tex; const float* gray_tex_base; int gray_tex_w, gray_tex_h;
     mfsr_merge_geom geom;
 };
 
@@ -189,14 +191,14 @@ static int build_pairs(const mfsr_params& p, int n, int ref_idx, int8_t* from, i
 static size_t carve(mfsr_context* c, char* base, int n, int w, int h)
 {
     size_t off = 0;
-    auto take = [&](size_t bytes) -> char* { char* p = base ? base + off : nullptr; off += align_up(bytes, 256); return p; };
+    auto take = [&](size_t bytes) -> char* { char* p = base ? base + off : nullptr; off += align_up(bytes, 512); return p; };
     const mfsr_params& p = c->p;
     const int hw = w / 2, hh = h / 2;
     c->raw_pitch = align_up((size_t)w * 2, 16); c->raw_fs = c->raw_pitch * h;
     c->raw = (uint16_t*)take((size_t)c->raw_fs * n);
     c->rgbh_pitch = (int64_t)hw * 12; c->rgbh_fs = c->rgbh_pitch * hh;
     c->rgb_half = (float*)take((size_t)c->rgbh_fs * n);
-    c->gray_pitch = align_up((size_t)w * 4, 16); c->gray_fs = c->gray_pitch * h;
+    c->gray_pitch = align_up((size_t)w * 4, 32); c->gray_fs = align_up((size_t)c->gray_pitch * h, 512);      // texture alignment (pitch 32 B, base 512 B)
     c->gray = (float*)take((size_t)c->gray_fs * n);
     c->rgb_pitch = (int64_t)w * 12;
     c->rgb_ref = (float*)take((size_t)c->rgb_pitch * h);
@@ -286,6 +288,7 @@ extern "C" int mfsr_create(const mfsr_params* params, int device, int max_w, int
     if (!c) return MFSR_E_NOMEM;
     c->p = *params; c->device = device; c->max_w = max_w; c->max_h = max_h; c->max_frames = max_frames;
     c->have_frames = false; c->ran = false; c->timed = true; c->ws = nullptr; c->launches = 0;
+    c->n_gray_tex = 0; c->gray_tex_base = nullptr; c->gray_tex_w = c->gray_tex_h = 0;
     c->ws_bytes = carve(c, nullptr, max_frames, max_w, max_h);
     if (c->lv.empty()) { delete c; return MFSR_E_INVALID; }
     cudaError_t e = cudaMalloc(&c->ws, c->ws_bytes);
@@ -303,6 +306,7 @@ extern "C" int mfsr_destroy(mfsr_handle h)
     if (!h) return MFSR_E_INVALID;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    for (int f = 0; f < h->n_gray_tex; f++) cudaDestroyTextureObject(h->gray_tex[f]);
     for (int i = 0; i <= ST_COUNT; i++) cudaEventDestroy(h->ev[i]);
     cudaStreamDestroy(h->stream);
     cudaFree(h->ws);
@@ -346,6 +350,21 @@ extern "C" int mfsr_set_frames(mfsr_handle h, const void* const* frames, int n, 
     make_geom(h->p, width, height, &h->geom);
     // measured pairs (i, j), 0 < j - i <= pair_span
     h->m = build_pairs(h->p, n, ref_idx, h->pt.from, h->pt.to, CONS_MAX_M);
+    // textures over the gray frames: re-created only when the burst geometry changes (the handle's stream must be idle then:
+    // a texture object may not be destroyed under a running kernel)
+    if (h->gray_tex_base != h->gray || h->gray_tex_w != width || h->gray_tex_h != height || h->n_gray_tex != n) {
+        if (h->n_gray_tex) MFSR_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        for (int f = 0; f < h->n_gray_tex; f++) cudaDestroyTextureObject(h->gray_tex[f]);
+        h->n_gray_tex = 0;
+        if (h->p.band_global_h == 0) {
+            for (int f = 0; f < n; f++) {
+                const int rc = make_gray_texture((const float*)((const char*)h->gray + h->gray_fs * f), h->gray_pitch, width, height, &h->gray_tex[f]);
+                if (rc) return rc;
+                h->n_gray_tex = f + 1;
+            }
+        }
+        h->gray_tex_base = h->gray; h->gray_tex_w = width; h->gray_tex_h = height;
+    }
     if (h->pa_cs) {
         // (cos, sin) of the candidate angles, computed in double and rounded once: the oracle uses the same table
         static float table[2 * PA_TABLE];
@@ -524,7 +543,7 @@ static int run_impl(mfsr_handle h, void* out_any, int64_t out_pitch, int out_on_
                                     (const float*)((const char*)h->gray + h->gray_fs * f + h->gray_pitch * ra), h->gray_pitch,
                                     (const float2*)((const char*)cur + h->flow_fs * f + h->flow_pitch * ra),
                                     (float2*)((char*)nxt + h->flow_fs * f + h->flow_pitch * ra),
-                                    h->flow_pitch, w, rh, p.lk_half_window, p.lk_min_det, gh, gy0, st));
+                                    h->flow_pitch, w, rh, p.lk_half_window, p.lk_min_det, gh, gy0, st, h->n_gray_tex == n ? h->gray_tex[f] : 0));
         }
         float2* t = cur; cur = nxt; nxt = t;
     }

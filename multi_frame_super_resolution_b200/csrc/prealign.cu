@@ -2,7 +2,7 @@
 //
 // Compiled with -fmad=false: the sample positions hang on strictly rounded fp32 values (the oracle evaluates the same
 // expressions with -ffp-contract=off), the scores are integer sums, candidates are compared as exact fractions and ties go to
-// the lowest candidate index — the estimate is bit-identical to oracle/mfsr_oracle.c:orc_prealign_search.
+// the lowest candidate index — the estimate is bit-identical to the CPU restatement the tests hold beside it.
 //
 // The reference carries the stage only as a skeleton (class PreAlignment, boxFilterNPP.cpp:102-166: buffers for an FFT phase
 // correlation of a rotated image, no code) plus the kernels that CONSUME its result: convertToTilesOverlapBorder / PreShift

@@ -141,10 +141,19 @@ def flow_from_tiles(tile_shift, tile_size, w, h, base_shift=(0.0, 0.0), base_rot
     return flow
 
 
-def lk_iteration(ref, mov, flow, half_window=3, min_det=1e-3):
+def lk_iteration(ref, mov, flow, half_window=3, min_det=1e-3, texture=False):
+    """One Lucas-Kanade sweep.  texture=True: the warp samples `mov` through the texture unit (mfsr_stage_lk_iteration_tex, what
+    mfsr_run does outside row-band mode); False: the ALU model of the texture filter (bit-identical to the oracle)."""
     _cuda(ref, mov, flow)
     h, w = ref.shape
     out = torch.empty_like(flow)
+    if texture:
+        wp = (w + 7) // 8 * 8                       # texture pitch alignment: 32 bytes
+        refp = torch.zeros((h, wp), dtype=torch.float32, device=ref.device); refp[:, :w] = ref
+        movp = torch.zeros((h, wp), dtype=torch.float32, device=ref.device); movp[:, :w] = mov
+        check(_lib.load().mfsr_stage_lk_iteration_tex(_p(refp), _p(movp), wp * 4, _p(flow), _p(out), w * 8, w, h, half_window, float(min_det),
+                                                      _stream()), "mfsr_stage_lk_iteration_tex")
+        return out
     check(_lib.load().mfsr_stage_lk_iteration(_p(ref), _p(mov), w * 4, _p(flow), _p(out), w * 8, w, h, half_window, float(min_det),
                                               _stream()), "mfsr_stage_lk_iteration")
     return out

@@ -300,16 +300,25 @@ def test_lk_iteration_vs_oracle(cuda_device, burst):
 
 @needs_ref
 def test_lk_iteration_vs_reference_kernels(cuda_device, burst):
+    """One sweep against WarpingKernel + ComputeDerivativesKernel + lucasKanadeOptim (opticalFlow.cu:28,97,190) on the same
+    buffers.  With the warp on the texture unit (what mfsr_run uses) the warped image is the reference's bit for bit and the flow
+    update differs only by the re-associated window sums and the MUFU pseudo-inverse; with the ALU model of the texture filter the
+    1.8 fixed-point fraction is off by one LSB on a few % of the fetches."""
     fr, sh = burst
     tr = _track(u16(fr[:2]))
     ref, mov = torch.from_numpy(tr[0][0]).to(cuda_device), torch.from_numpy(tr[1][0]).to(cuda_device)
     h, w = ref.shape
+    ys, xs = torch.meshgrid(torch.arange(h, device=cuda_device, dtype=torch.float32), torch.arange(w, device=cuda_device, dtype=torch.float32), indexing="ij")
     flow = torch.zeros((h, w, 2), device=cuda_device)
-    flow[..., 0], flow[..., 1] = -sh[1, 0].item() + 0.3, -sh[1, 1].item() - 0.2
-    got = stages.lk_iteration(ref, mov, flow, 3, 1e-3)
+    flow[..., 0] = -sh[1, 0].item() + 0.3 + 0.4 * torch.sin(xs / 23.0)
+    flow[..., 1] = -sh[1, 1].item() - 0.2 + 0.3 * torch.cos(ys / 31.0)
     exp = pyref.lk_iteration(ref, mov, flow, 3, 1e-3)
-    d = (got - exp).abs()
-    assert float(torch.quantile(d.flatten()[:: 7], 0.999)) <= 2e-2     # texture-unit bilinear in the warp
+    got_tex = stages.lk_iteration(ref, mov, flow, 3, 1e-3, texture=True)
+    d = (got_tex - exp).abs().flatten()
+    assert float(torch.quantile(d[::7], 0.999)) <= 2e-3, float(d.max())
+    got_alu = stages.lk_iteration(ref, mov, flow, 3, 1e-3)
+    d = (got_alu - exp).abs().flatten()
+    assert float(torch.quantile(d[::7], 0.999)) <= 2e-2
 
 
 def test_kernel_params_vs_oracle(cuda_device, burst):
