@@ -130,7 +130,11 @@ typedef struct mfsr_params {
      * levels of the tracking pyramid) and feed it to the tile matcher and the flow field as their baseShift / baseRotation
      * (kernel.cu:275-276, opticalFlow.cu:57-58) per pair / per frame; it then replaces base_shift / base_rotation.  0 = off. */
     int   prealign;
-    int   reserved[2];
+    /* 1: the Lucas-Kanade warp samples the moved frame through the texture unit, exactly as the reference's WarpingKernel does
+     * (opticalFlow.cu:36-41; hardware 1.8 fixed-point filter: bit-identical to the reference kernels, ~0.4 ms faster per 12 MP
+     * burst).  0 (default): the ALU model of that filter, bit-identical to the CPU restatement and across row bands. */
+    int   lk_texture;
+    int   reserved[1];
 } mfsr_params;
 
 int         mfsr_abi_version(void);

@@ -38,7 +38,7 @@ class Params(C.Structure):
         ("tensor_box_radius", c_i),
         ("alpha", c_f), ("beta", c_f), ("thresholdM", c_f), ("mask_erode_radius", c_i),
         ("weight_threshold", c_f), ("merge_flags", c_i),
-        ("band_global_h", c_i), ("band_row0", c_i), ("band_keep_row0", c_i), ("band_keep_rows", c_i), ("band_margin", c_i), ("prealign", c_i), ("reserved", c_i * 2),
+        ("band_global_h", c_i), ("band_row0", c_i), ("band_keep_row0", c_i), ("band_keep_rows", c_i), ("band_margin", c_i), ("prealign", c_i), ("lk_texture", c_i), ("reserved", c_i * 1),
     ]
 
 

@@ -162,7 +162,7 @@ static int validate_params(const mfsr_params* p)
     if (p->lk_iterations < 0 || p->lk_half_window < 1 || p->lk_half_window > 4) return MFSR_E_INVALID;
     if (p->tensor_box_radius < 0 || p->tensor_box_radius > 3 || p->mask_erode_radius < 0 || p->mask_erode_radius > 8) return MFSR_E_INVALID;
     for (int i = 0; i < 4; i++) if (p->cfa[i] < 0 || p->cfa[i] > 2) return MFSR_E_INVALID;
-    if (p->prealign != 0 && p->prealign != 1) return MFSR_E_INVALID;
+    if ((p->prealign != 0 && p->prealign != 1) || (p->lk_texture != 0 && p->lk_texture != 1)) return MFSR_E_INVALID;
     if (p->band_global_h < 0 || p->band_row0 < 0 || p->band_keep_row0 < 0 || p->band_keep_rows < 0 || p->band_margin < 0) return MFSR_E_INVALID;
     if (p->band_global_h > 0) {
         const int grid = p->tile_size << (p->levels - 1);
@@ -356,7 +356,7 @@ extern "C" int mfsr_set_frames(mfsr_handle h, const void* const* frames, int n, 
         if (h->n_gray_tex) MFSR_CUDA_TRY(cudaStreamSynchronize(h->stream));
         for (int f = 0; f < h->n_gray_tex; f++) cudaDestroyTextureObject(h->gray_tex[f]);
         h->n_gray_tex = 0;
-        if (h->p.band_global_h == 0) {
+        if (h->p.band_global_h == 0 && h->p.lk_texture) {
             for (int f = 0; f < n; f++) {
                 const int rc = make_gray_texture((const float*)((const char*)h->gray + h->gray_fs * f), h->gray_pitch, width, height, &h->gray_tex[f]);
                 if (rc) return rc;

@@ -45,7 +45,7 @@ def test_default_params_layout():
     assert p.tile_size == 16 and p.max_shift == 4 and p.track_bits == 7 and p.pair_span == 2
     assert abs(p.track_sigma - 0.5) < 1e-7 and abs(p.weight_threshold - 0.1) < 1e-7
     assert abs(p.thresholdM - 0.8) < 1e-7 and p.mask_erode_radius == 2 and p.lk_half_window == 3
-    assert p.band_global_h == 0 and p.band_keep_rows == 0 and p.band_margin == 0 and p.prealign == 0 and list(p.reserved) == [0] * 2                      # struct size matches: the tail is still zero
+    assert p.band_global_h == 0 and p.band_keep_rows == 0 and p.band_margin == 0 and p.prealign == 0 and p.lk_texture == 0 and list(p.reserved) == [0]                      # struct size matches: the tail is still zero
     assert lib.mfsr_default_params(None) == -1
 
 
