@@ -1,5 +1,6 @@
 """Data-parallel host logic: independent bursts shard across ranks with NO data-path collective.
 
+Used by bench.py (--mode dp) and covered under gloo by tests/test_dp_cpu.py; the row-band split of ONE large burst lives in rowband.py.
 The reference is single-GPU (cudaSetDevice(0), test_opencv/kernel.cu:45).  Bursts are independent
 units, so burst b simply goes to rank b mod G; the only communication is the
 aggregation of the timing/throughput scalars, which works on any torch.distributed backend
@@ -36,19 +37,3 @@ def aggregate_throughput(local_units: float, local_ms: float, device="cpu"):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     return float(u.item()), ms, (float(u.item()) / (ms / 1e3) if ms > 0 else float("inf"))
-
-
-def row_bands(height: int, world: int, align: int, halo: int):
-    """Row-band split of ONE large burst (SURVEY §8e case 2): contiguous bands aligned to `align`
-    rows (tile rows of the coarsest pyramid level), each extended by `halo` rows that the owner
-    reads from its neighbours.  Returns [(own_lo, own_hi, read_lo, read_hi)] per rank."""
-    if world < 1 or align < 1 or height < world * align:
-        raise ValueError("image too small for this many bands")
-    units = height // align
-    bands, lo = [], 0
-    for r in range(world):
-        cnt = units // world + (1 if r < units % world else 0)
-        hi = height if r == world - 1 else lo + cnt * align
-        bands.append((lo, hi, max(0, lo - halo), min(height, hi + halo)))
-        lo = hi
-    return bands

@@ -20,8 +20,16 @@ from typing import List
 import torch
 
 DEFAULT_HALO = 256     # rows; two coarsest-level tiles (2 x 128 rows) cover the matcher's footprint at 4 levels
-DEFAULT_MARGIN = 64    # rows beyond the kept rows on which flow / kernel parameters / robustness are evaluated (mfsr_params.band_margin):
-                       # stencil footprints (LK 3 x 5 rows, robustness 12) + vertical flows up to ~35 rows
+DEFAULT_MARGIN = 64    # legacy margin (covers vertical flows up to ~35 rows); default_margin(params) derives the safe one
+
+
+def default_margin(params) -> int:
+    """Rows beyond the kept rows on which flow / kernel parameters / robustness must be evaluated (mfsr_params.band_margin) so that
+    the kept rows cannot see the band's edge: stencil footprints (LK 3 sweeps x 5 rows + robustness 12 = 27 rows) plus the largest
+    vertical flow the aligner can produce per measured pair, max_shift * (2^levels - 1), plus the global base shift; rounded up to
+    the LK tile height (32).  With a smaller margin large vertical motion silently clamps at the band's edge."""
+    reach = 27 + int(params.max_shift) * ((1 << int(params.levels)) - 1) + int(abs(params.base_shift[1]) + 0.999)
+    return (reach + 31) // 32 * 32
 
 
 @dataclass(frozen=True)
@@ -104,10 +112,11 @@ def exchange_halos(own: torch.Tensor, bands: List[Band], rank: int, group=None) 
     return out.view(dtype)
 
 
-def band_params(params, band: Band, global_height: int, margin: int = DEFAULT_MARGIN):
-    """Copy of `params` switched to row-band mode for `band`.  margin = 0 evaluates every stage on the whole band + halo."""
+def band_params(params, band: Band, global_height: int, margin=None):
+    """Copy of `params` switched to row-band mode for `band`.  margin = 0 evaluates every stage on the whole band + halo; None derives
+    the margin from the params (default_margin)."""
     p = type(params).from_buffer_copy(params)
-    p.band_margin = int(margin)
+    p.band_margin = int(default_margin(params) if margin is None else margin)
     p.full_frame = 1
     p.band_global_h = int(global_height)
     p.band_row0 = int(band.top)

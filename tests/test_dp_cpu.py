@@ -20,17 +20,6 @@ def test_shard_bursts_partition():
     assert dp.burst_seed(1234, 7) == 1241
 
 
-def test_row_bands_cover_and_align():
-    bands = dp.row_bands(6048, 8, 128, 72)
-    assert bands[0][0] == 0 and bands[-1][1] == 6048
-    for (lo, hi, rlo, rhi), nxt in zip(bands, bands[1:] + [None]):
-        assert lo % 128 == 0 and rlo == max(0, lo - 72) and rhi == min(6048, hi + 72)
-        if nxt:
-            assert hi == nxt[0]
-    with pytest.raises(ValueError):
-        dp.row_bands(100, 8, 128, 4)
-
-
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)

@@ -66,5 +66,7 @@ def test_band_params_fields():
     bands = rowband.plan_bands(6048, 8, p.tile_size << (p.levels - 1), 256)
     assert [b.rows for b in bands] == [768] * 7 + [672]
     bp = rowband.band_params(p, bands[3], 6048)
-    assert (bp.band_global_h, bp.band_row0, bp.band_keep_row0, bp.band_keep_rows, bp.band_margin) == (6048, 3 * 768 - 256, 256, 768, rowband.DEFAULT_MARGIN)
+    assert (bp.band_global_h, bp.band_row0, bp.band_keep_row0, bp.band_keep_rows, bp.band_margin) == (6048, 3 * 768 - 256, 256, 768, rowband.default_margin(p))
+    # stencils 27 rows + the aligner's reach 4 * (2^4 - 1) = 60 rows, rounded up to the LK tile height
+    assert rowband.default_margin(p) == 96
     assert p.band_global_h == 0 and rowband.band_params(p, bands[0], 6048, margin=0).band_margin == 0     # the input params are not modified

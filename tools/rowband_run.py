@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--height", type=int, default=6048); ap.add_argument("--width", type=int, default=8064)
     ap.add_argument("--frames", type=int, default=15); ap.add_argument("--halo", type=int, default=rowband.DEFAULT_HALO)
     ap.add_argument("--steps", type=int, default=3); ap.add_argument("--verify", action="store_true")
-    ap.add_argument("--margin", type=int, default=rowband.DEFAULT_MARGIN)
+    ap.add_argument("--margin", type=int, default=-1, help="-1: derived from the params (rowband.default_margin)")
     a = ap.parse_args()
     rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
@@ -37,6 +37,7 @@ def main():
     if not a.verify:
         del full
     torch.cuda.synchronize(dev)
+    a.margin = rowband.default_margin(p) if a.margin < 0 else a.margin
     bp = rowband.band_params(p, b, a.height, a.margin)
     sr = BurstSuperResolution(bp, device=lr, max_width=a.width, max_height=b.bottom - b.top, max_frames=a.frames)
     ow, oh = sr.output_size(a.width, b.bottom - b.top)
