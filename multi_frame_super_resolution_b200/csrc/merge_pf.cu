@@ -44,10 +44,12 @@ template <int TH> struct PCfg {
     static constexpr int KWS = TW / 2 + 2, KHS = TH / 2 + 2;
     static constexpr int KERN_BYTES = KWS * KHS * 16;
     static constexpr int VN = 2 * (RWS - 2), UN = 2 * (RHS - 2);      // valid table indices; entry [VN] / [UN] is the poison
-    static constexpr int TAB_BYTES = ((VN + 1 + UN + 1) * 4 + 15) & ~15;
+    static constexpr int TAB_BYTES = ((VN + 1 + UN + 1) * 4 + 127) & ~127;
+    static constexpr int OT_ROW_BYTES = TW * 12;                  // one output row of the tile (float3)
+    static constexpr int OT_BYTES = TH * OT_ROW_BYTES;            // fallback-in / result-out tile moved by TMA bulk copies
     static_assert(MHS * MWS * 8 <= PLANE_BYTES, "certainty plane does not fit its slot");
     static_assert((RHS - 3) * RWS * 4 + (RHALF + RHALF) * 4 < (int)SPECIAL, "raw window offsets collide with the special range");
-    static size_t smem_bytes(int n) { return (size_t)n * (DESC_BYTES + RAW_BYTES + MASK_FRAME_BYTES) + KERN_BYTES + TAB_BYTES; }
+    static size_t smem_bytes(int n, bool tma) { return (size_t)n * (DESC_BYTES + RAW_BYTES + MASK_FRAME_BYTES) + KERN_BYTES + TAB_BYTES + (tma ? OT_BYTES : 0); }
 };
 
 __device__ __forceinline__ float4 lds_f4(unsigned addr)
@@ -56,6 +58,39 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr)
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+
+// ---- TMA bulk copies (cp.async.bulk, Hopper+ / sm_100a) for the tile's fallback rows (in) and result rows (out): pure copies of
+// 1536-byte row segments that the per-pixel code otherwise moved as 3 + 3 scalar accesses with a 48-byte lane stride (32 sectors per
+// warp instruction).  One elected thread issues them; completion of the loads is tracked by an mbarrier, of the stores by a bulk group.
+__device__ __forceinline__ void mbar_init(unsigned mbar_s, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_s), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar_s, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar_s, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(mbar_s), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_row(unsigned dst_s, const void* src, unsigned bytes, unsigned mbar_s)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_s), "l"(src), "r"(bytes), "r"(mbar_s) : "memory");
+}
+__device__ __forceinline__ void tma_store_row(void* dst, unsigned src_s, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // 13 regression weights of absolute HR pixel (X, Y) (:401, :427-430) from the staged kernel-parameter window
 // (float4 [KHS][KWS], origin (kx0, ky0) in raw coordinates, clamp addressing applied while staging).
@@ -269,7 +304,7 @@ __device__ __forceinline__ void frame_loop(const FastArgs& F, int N, const unsig
 // (weights) and epilogue (CFA phase -> colour, ApplyWeighting kernel.cu:426, GammasRGB :393, one write) exist once; only the
 // frame loop is specialised (16 copies selected by a switch).
 template <int TH>
-__device__ __forceinline__ void run_row(const FastArgs& F, const unsigned char* smem, int row, int x0, int y0, int X0abs, int Y0abs)
+__device__ __forceinline__ void run_row(const FastArgs& F, const unsigned char* smem, int row, int x0, int y0, int X0abs, int Y0abs, float* ot_row)
 {
     using C = PCfg<TH>;
     const MergeArgs& A = F.a;
@@ -297,7 +332,8 @@ __device__ __forceinline__ void run_row(const FastArgs& F, const unsigned char* 
         const int x = x0 + 4 * lane + J, X = X0abs + 4 * lane + J;
         if (x < F.in_x0 || x >= F.in_x1) continue;            // outside the window or in the clamp band (merge_band_kernel's pixels)
         float fb3[3] = {0.f, 0.f, 0.f};         // ApplyWeighting's inOutImg value, fetched early: its latency hides behind the frame loop
-        if (A.fallback) { const float* fbp = row_ptr(A.fallback, A.fb_pitch, y) + 3 * x; fb3[0] = __ldg(fbp); fb3[1] = __ldg(fbp + 1); fb3[2] = __ldg(fbp + 2); }
+        // ot_row != null: the tile's fallback rows were brought to shared memory by TMA (and the result leaves the same way)
+        if (!ot_row && A.fallback) { const float* fbp = row_ptr(A.fallback, A.fb_pitch, y) + 3 * x; fb3[0] = __ldg(fbp); fb3[1] = __ldg(fbp + 1); fb3[2] = __ldg(fbp + 2); }
         float acc[4] = {0.f, 0.f, 0.f, 0.f}, wacc[4] = {0.f, 0.f, 0.f, 0.f};
         {
             float W[mt::NW];
@@ -331,9 +367,15 @@ __device__ __forceinline__ void run_row(const FastArgs& F, const unsigned char* 
             for (int c = 0; c < 3; c++) { so[c] = s3[c]; wo[c] = w3[c]; }
         }
         if (!(A.flags & MFSR_MERGE_PARTIAL_INTERNAL)) {
-            float* orow = row_ptr(A.out, A.out_pitch, y);
+            if (ot_row) {
+                float* o = ot_row + 3 * (4 * lane + J);
 #pragma unroll
-            for (int c = 0; c < 3; c++) orow[3 * x + c] = finish_px(apply_weighting(s3[c], w3[c], fb3[c], A.threshold), A.flags);
+                for (int c = 0; c < 3; c++) o[c] = finish_px(apply_weighting(s3[c], w3[c], o[c], A.threshold), A.flags);
+            } else {
+                float* orow = row_ptr(A.out, A.out_pitch, y);
+#pragma unroll
+                for (int c = 0; c < 3; c++) orow[3 * x + c] = finish_px(apply_weighting(s3[c], w3[c], fb3[c], A.threshold), A.flags);
+            }
         }
     }
 }
@@ -631,13 +673,19 @@ merge_pf_kernel(const __grid_constant__ FastArgs F, int tiles_x, int n_tiles)
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int2 fbase[MAXF];           // origin (rx0, ry0) of the staged raw window per frame
     __shared__ int s_border;               // 1: some pixel-frame of the tile may touch the clamp range
+    __shared__ __align__(8) unsigned long long s_mbar[TH];  // completion of each row's TMA fallback load (a warp owns a row)
     const MergeArgs& A = F.a;
     const mfsr_merge_geom& g = A.g;
     const int N = A.n_frames;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned mbar_s = (unsigned)__cvta_generic_to_shared(&s_mbar[warp]);
+    if (lane == 0) mbar_init(mbar_s, 1);
+    __syncwarp();
+    unsigned tma_phase = 0;
     unsigned char* kernS = smem + (size_t)N * (C::DESC_BYTES + C::RAW_BYTES + MASK_FRAME_BYTES);
     unsigned* colT = (unsigned*)(kernS + C::KERN_BYTES);
     unsigned* rowT = colT + C::VN + 1;
+    float* otS = (float*)(kernS + C::KERN_BYTES + C::TAB_BYTES);
 
     // ---------------- lookup tables of phase 0 (same for every tile and frame: indices are relative to the window origin)
     for (int i = tid; i <= C::VN + C::UN + 1; i += C::NT) {
@@ -660,6 +708,18 @@ merge_pf_kernel(const __grid_constant__ FastArgs F, int tiles_x, int n_tiles)
         // window equals the absolute row parity)
         if (tid == 0) s_border = 0;
         __syncthreads();                   // also: the previous tile's frame loops are done with the shared-memory windows
+        // ---------------- TMA: the warp's fallback row on its way to shared memory (needed by the epilogues, long after).  Everything
+        // about a row (load, mbarrier, result, store) belongs to the warp that owns it: no block-level synchronisation is added.
+#ifdef MFSR_PF_NO_TMA
+        const bool tma = false;
+#else
+        const bool tma = F.use_tma && x0 >= 0 && x0 + TW <= g.out_w && y0 + warp >= 0 && y0 + warp < g.out_h;     // a whole row segment inside the image
+#endif
+        float* ot_row = otS + warp * (TW * 3);
+        if (tma && lane == 0) {
+            mbar_expect_tx(mbar_s, (unsigned)C::OT_ROW_BYTES);
+            tma_load_row((unsigned)__cvta_generic_to_shared(ot_row), row_ptr(A.fallback, A.fb_pitch, y0 + warp) + 3 * x0, C::OT_ROW_BYTES, mbar_s);
+        }
         for (int f = warp; f < N; f += C::NW_) {
             const float2* flow = (const float2*)((const char*)A.flow + A.flow_fs * f);
             const int sxp = clampi((X0abs >> 1) + 4 + 8 * (lane & 7), 0, g.raw_w - 1);
@@ -694,7 +754,17 @@ merge_pf_kernel(const __grid_constant__ FastArgs F, int tiles_x, int n_tiles)
             if (nt < n_tiles) prefetch_tile<TH>(F, (nt % tiles_x) * TW - F.x_off, (nt / tiles_x) * TH - F.y_off);
         }
         // ---------------- phase 2: warp w owns tile row w: four passes J = 0..3, each a loop over the frames
-        run_row<TH>(F, smem, warp, x0, y0, X0abs, Y0abs);
+        if (tma) { mbar_wait(mbar_s, tma_phase); tma_phase ^= 1u; }
+        run_row<TH>(F, smem, warp, x0, y0, X0abs, Y0abs, tma ? ot_row : nullptr);
+        if (tma) {
+            // ---------------- TMA: the finished row leaves as one bulk store (the warp's generic-proxy writes made visible to the async proxy)
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_row(row_ptr(A.out, A.out_pitch, y0 + warp) + 3 * x0, (unsigned)__cvta_generic_to_shared(ot_row), C::OT_ROW_BYTES);
+                tma_store_commit_wait();
+            }
+        }
     }
 }
 
@@ -786,7 +856,19 @@ int launch_th(const FastArgs& Fin, cudaStream_t st)
     using C = PCfg<TH>;
     FastArgs F = Fin;
     const mfsr_merge_geom& g = F.a.g;
-    const size_t smem = C::smem_bytes(F.a.n_frames);
+    // TMA bulk copies of the fallback / result rows (cp.async.bulk + mbarrier, one row per warp) need 16-byte aligned row segments:
+    // window origin on the tile grid, pitches and bases multiples of 16, a fallback image, and an image (not only partial sums) to
+    // write.  OFF by default: measured on one box (tools/ab_merge.sh, 12 MP x 8) the kernel takes 5.90 ms with them against 5.66 ms
+    // without — the fallback loads were already hidden behind the frame loop, the bulk store adds a proxy fence and a wait per warp,
+    // and the 24.5 KB tile buffer comes out of the L1 that the staging loads use.  MFSR_PF_TMA=1 switches them on.
+    {
+        static const char* te = getenv("MFSR_PF_TMA");
+        const bool want = te && te[0] == '1';
+        F.use_tma = want && F.x_off == 0 && F.a.fallback && !(F.a.flags & MFSR_MERGE_PARTIAL_INTERNAL) &&
+                    !(((uintptr_t)F.a.fallback | (uintptr_t)F.a.out | (uintptr_t)F.a.fb_pitch | (uintptr_t)F.a.out_pitch) & 15);
+    }
+    if (F.use_tma && C::smem_bytes(F.a.n_frames, true) > (size_t)225 * 1024) F.use_tma = 0;      // the tile buffer does not fit beside this many frames
+    const size_t smem = C::smem_bytes(F.a.n_frames, F.use_tma != 0);
     // opt-in shared memory (227 KB per block on sm_100 minus this instantiation's static tables); the attribute belongs to the
     // current device's context, so it is set per device (a function-static flag broke the second GPU of a process)
     static size_t max_dyn[64] = {0};

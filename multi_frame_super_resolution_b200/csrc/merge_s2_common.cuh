@@ -25,6 +25,7 @@ struct FastArgs {
     float cfa_sel[4][3];         // 1 / 0: CFA phase q has colour c (certainty staging of merge_pf.cu)
     float nbi_ph[4];             // -black * 1/white per CFA phase (raw staging of merge_pf.cu)
     int in_x0, in_x1, in_y0, in_y1;   // merge_pf.cu: the tile kernel's pixels (window coordinates); the rest is the clamp band's
+    int use_tma;                 // merge_pf.cu: fallback / result rows of a tile move by TMA bulk copies
 };
 
 // merge_pf.cu: the predicate-free slot kernel (16-row tiles) and the number of frames it keeps resident

@@ -12,6 +12,8 @@
 #include <vector>
 #include <math.h>
 
+namespace mfsr { namespace s2 { int merge_pf_capacity(); } }      // frames the scale-2 merge kernel keeps resident (merge_pf.cu)
+
 using namespace mfsr;
 
 namespace {
@@ -215,7 +217,7 @@ static size_t carve(mfsr_context* c, char* base, int n, int w, int h)
     c->fallback = (float*)take((size_t)c->out_pitch_own * (g.out_h + 2));      // + 2: a band's merge window grows by one
     c->outbuf = (float*)take((size_t)c->out_pitch_own * (g.out_h + 2));        //      row at each interior seam
     c->part_sum = c->part_weight = nullptr;
-    if (n > 10 && p.scale == 2) {                 // more frames than the 16-row merge tile holds at once: merge in chunks of frames (merge_dyn.cu)
+    if (n > s2::merge_pf_capacity() && p.scale == 2) {      // more frames than the merge tile holds at once: merged in chunks of frames (partial sums)
         c->part_sum = (float*)take((size_t)c->out_pitch_own * (g.out_h + 2));
         c->part_weight = (float*)take((size_t)c->out_pitch_own * (g.out_h + 2));
     }
