@@ -14,6 +14,11 @@
 //   sets its Lucas-Kanade sweeps (:181 setIterations).
 // * like the reference, the burst is processed num_times = 10 times and the last real_times = 5 are timed (:146-149,:188-203);
 //   prints "<t> sec" and "<fps> FPS" (:204-205), writes <input>_<flow>_sr_result.ppm and the sharpened _sr2_result.ppm (:206-209).
+// * `--radius R` (anywhere on the command line) selects the reference's temporal-area pull mode (:182 setTemporalAreaRadius(1),
+//   :185-194): the source is the frame set repeated num_times (:168-176), every nextFrame() returns the super-resolved frame i
+//   merged from frames [i - R, i + R] (clipped at the ends of the sequence) until the sequence is exhausted, the frames from
+//   start_i = (num_times - real_times) * num_images on are timed (:167,:188-190).  Without it the whole frame set is one burst
+//   merged onto its first frame (the BASELINE configurations).
 #include "mfsr.h"
 
 #include <algorithm>
@@ -115,13 +120,15 @@ std::vector<unsigned char> sharpen(const std::vector<unsigned char>& img, int w,
 // nullptr when exhausted, reset() rewinds.
 class BurstFrameSource {
 public:
-    explicit BurstFrameSource(std::vector<RawFrame> frames) : frames_(std::move(frames)) {}
-    const RawFrame* nextFrame() { return index_ < frames_.size() ? &frames_[index_++] : nullptr; }
+    // `repeat`: the reference fills its vector with the frame set num_times over (:168-176); here the set is stored once
+    explicit BurstFrameSource(std::vector<RawFrame> frames, size_t repeat = 1) : frames_(std::move(frames)), repeat_(repeat) {}
+    const RawFrame* nextFrame() { return index_ < size() ? &frames_[index_++ % frames_.size()] : nullptr; }
     void reset() { index_ = 0; }
-    size_t size() const { return frames_.size(); }
+    size_t size() const { return frames_.size() * repeat_; }
 private:
     size_t index_ = 0;
     std::vector<RawFrame> frames_;
+    size_t repeat_;
 };
 
 // The slice of cv::superres::SuperResolution the reference program uses (:179-194), on top of one mfsr handle.
@@ -130,33 +137,49 @@ public:
     ~BurstSuperResolution() { if (h_) mfsr_destroy(h_); }
     void setScale(int s) { scale_ = s; }
     void setIterations(int it) { iterations_ = it; }
-    void setInput(BurstFrameSource* src) { src_ = src; }
+    void setTemporalAreaRadius(int r) { radius_ = r; seq_.clear(); pos_ = 0; }      // r < 0: the whole source is one burst
+    void setInput(BurstFrameSource* src) { src_ = src; seq_.clear(); pos_ = 0; }
     int outWidth() const { return ow_; }
     int outHeight() const { return oh_; }
-    // pulls the whole burst from the source (temporal area = the burst) and produces the 8-bit sRGB image
+    // Produces the next 8-bit sRGB image; `result` comes back EMPTY (return 0) once a temporal-area sequence is exhausted,
+    // like the reference's result.empty() (:191).
     int nextFrame(std::vector<unsigned char>& result)
     {
         if (!src_) return MFSR_E_STATE;
-        src_->reset();
-        std::vector<const void*> ptrs;
-        const RawFrame* first = nullptr;
-        while (const RawFrame* f = src_->nextFrame()) {
-            if (!first) first = f;
-            if (f->w != first->w || f->h != first->h) return MFSR_E_INVALID;
-            ptrs.push_back(f->px.data());
+        if (seq_.empty() || radius_ < 0) {               // pull the source once (temporal mode) / once per burst
+            src_->reset();
+            seq_.clear();
+            pos_ = 0;
+            while (const RawFrame* f = src_->nextFrame()) {
+                if (!seq_.empty() && (f->w != seq_[0]->w || f->h != seq_[0]->h || f->gray != seq_[0]->gray)) return MFSR_E_INVALID;
+                seq_.push_back(f);
+            }
+            if (seq_.empty()) return MFSR_E_INVALID;
         }
-        if (!first) return MFSR_E_INVALID;
+        const RawFrame* first = seq_[0];
+        const size_t n = seq_.size();
+        size_t lo = 0, hi = n, ref = 0;
+        if (radius_ >= 0) {
+            if (pos_ >= n) { result.clear(); return 0; }
+            lo = pos_ > (size_t)radius_ ? pos_ - radius_ : 0;
+            hi = std::min(n, pos_ + radius_ + 1);
+            ref = pos_ - lo;
+            pos_++;
+        }
+        std::vector<const void*> ptrs;
+        for (size_t i = lo; i < hi; i++) ptrs.push_back(seq_[i]->px.data());
         if (!h_) {
             mfsr_params p;
             mfsr_default_params(&p);
             p.scale = scale_; p.lk_iterations = iterations_; p.merge_flags = MFSR_MERGE_GAMMA;
             while (p.levels > 1 && (std::min(first->w, first->h) >> (p.levels - 1)) < 2 * p.max_shift + p.tile_size) p.levels--;
-            const int rc = mfsr_create(&p, 0, first->w, first->h, (int)ptrs.size(), &h_);
+            const int cap = radius_ >= 0 ? 2 * radius_ + 1 : (int)n;
+            const int rc = mfsr_create(&p, 0, first->w, first->h, cap, &h_);
             if (rc) return rc;
             mfsr_output_size(h_, first->w, first->h, &ow_, &oh_);
         }
         int rc = mfsr_set_frames(h_, ptrs.data(), (int)ptrs.size(), first->w, first->h, (int64_t)first->w * 2,
-                                 first->gray ? MFSR_FMT_GRAY_U16 : MFSR_FMT_BAYER_U16, 0, /*on_host*/1);
+                                 first->gray ? MFSR_FMT_GRAY_U16 : MFSR_FMT_BAYER_U16, (int)ref, /*on_host*/1);
         if (rc) return rc;
         result.resize((size_t)ow_ * oh_ * 3);
         return mfsr_run_format(h_, result.data(), (int64_t)ow_ * 3, /*out_on_host*/1, MFSR_OUT_U8, /*async*/0);
@@ -164,15 +187,18 @@ public:
 private:
     mfsr_handle h_ = nullptr;
     BurstFrameSource* src_ = nullptr;
-    int scale_ = 2, iterations_ = 3, ow_ = 0, oh_ = 0;
+    std::vector<const RawFrame*> seq_;
+    size_t pos_ = 0;
+    int scale_ = 2, iterations_ = 3, radius_ = -1, ow_ = 0, oh_ = 0;
 };
 
 void usage()
 {
-    printf("./multi_frame_sr_b200 optFlowName inputName iterations [frames]\n");
+    printf("./multi_frame_sr_b200 [--radius R] optFlowName inputName iterations [frames]\n");
     printf("\toptFlowName: farneback, tvl1, brox, pyrlk (accepted for compatibility)\n");
     printf("\tinputName: city, car, iso, or a printf pattern of .pgm/.ppm frames with [frames]\n");
     printf("\titerations: integer, 1, 10, etc.\n");
+    printf("\t--radius R: temporal-area mode (the reference uses 1): one result per frame from frames [i-R, i+R]\n");
 }
 
 }  // namespace
@@ -180,7 +206,15 @@ void usage()
 int main(int argc, char** argv)
 {
     std::string flow = "farneback", input = "city";
-    int iterations = 10, n_override = 0;
+    int iterations = 10, n_override = 0, radius = -1;
+    for (int i = 1; i + 1 < argc; i++) {
+        if (strcmp(argv[i], "--radius") == 0) {
+            radius = atoi(argv[i + 1]);
+            for (int j = i; j + 2 < argc; j++) argv[j] = argv[j + 2];
+            argc -= 2;
+            break;
+        }
+    }
     if (argc == 4 || argc == 5) {
         flow = argv[1]; input = argv[2]; iterations = atoi(argv[3]);
         if (iterations < 1) iterations = 1;
@@ -218,17 +252,33 @@ int main(int argc, char** argv)
         printf("cannot read %s(.pgm|.ppm)\n", buf);
         return -1;
     }
-    BurstFrameSource source(std::move(frames));
+    BurstFrameSource source(std::move(frames), radius >= 0 ? num_times : 1);
     BurstSuperResolution sr;
     sr.setScale(scale);
     sr.setIterations(iterations);
+    sr.setTemporalAreaRadius(radius);
     sr.setInput(&source);
-    std::vector<unsigned char> result;
+    std::vector<unsigned char> result, last;
     std::chrono::steady_clock::time_point t0;
-    for (int t = 0; t < num_times; t++) {
-        if (t == num_times - real_times) t0 = std::chrono::steady_clock::now();
-        const int rc = sr.nextFrame(result);
-        if (rc) { fprintf(stderr, "mfsr: %s (%d)\n", mfsr_error_string(rc), rc); return 1; }
+    double produced = 0;                       // results inside the timed part
+    if (radius >= 0) {
+        const int start_i = (num_times - real_times) * num_images;
+        for (int i = 0; i < num_images * num_times; i++) {
+            if (i == start_i) t0 = std::chrono::steady_clock::now();
+            const int rc = sr.nextFrame(result);
+            if (rc) { fprintf(stderr, "mfsr: %s (%d)\n", mfsr_error_string(rc), rc); return 1; }
+            if (result.empty()) break;
+            if (i >= start_i) produced += 1;
+            last.swap(result);
+        }
+        result.swap(last);
+    } else {
+        for (int t = 0; t < num_times; t++) {
+            if (t == num_times - real_times) t0 = std::chrono::steady_clock::now();
+            const int rc = sr.nextFrame(result);
+            if (rc) { fprintf(stderr, "mfsr: %s (%d)\n", mfsr_error_string(rc), rc); return 1; }
+        }
+        produced = real_times;
     }
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     printf("%g sec\n", sec);
@@ -239,7 +289,9 @@ int main(int argc, char** argv)
         fprintf(stderr, "cannot write the result images\n");
         return 1;
     }
-    printf("{\"output_megapixels_per_second\": %.2f, \"frames\": %d, \"out\": [%d, %d], \"scale\": %d, \"lk_iterations\": %d}\n",
-           real_times * (double)ow * oh / 1e6 / sec, num_images, ow, oh, scale, iterations);
+    printf("{\"output_megapixels_per_second\": %.2f, \"frames\": %d, \"out\": [%d, %d], \"scale\": %d, \"lk_iterations\": %d, "
+           "\"temporal_radius\": %d}\n",
+           produced * (double)ow * oh / 1e6 / sec, radius >= 0 ? std::min(num_images * num_times, 2 * radius + 1) : num_images, ow, oh, scale,
+           iterations, radius);
     return 0;
 }

@@ -14,6 +14,9 @@ Mirrors finalProject/Project/multi_frame_sr.cpp:122-209:
   prints "<t> sec" and "<fps> FPS" (:204-206), writes <input>_<flow>_sr_result.png and the Laplacian-sharpened
   <input>_<flow>_sr2_result.png (:90-119, :207-209), plus one JSON line with MP/s.
   (`host/multi_frame_sr_b200.cpp` is the same program in C++ over the C ABI, with Netpbm files.)
+* `--radius R` selects the reference's temporal-area pull mode (:182 setTemporalAreaRadius(1), :185-194): the frame set repeated
+  num_times is one sequence, every nextFrame() is the super-resolved frame i merged from frames [i - R, i + R], and the frames
+  from start_i = (num_times - real_times) * num_images on are timed.  Without it the frame set is one burst merged onto frame 0.
 
 8-bit colour frames are mosaiced to RGGB and mapped to the 10-bit range of the default parameters
 (raw = round(v8 * 959 / 255) + 64), exactly like tests/golden/make_bundled_fixture.py.
@@ -57,6 +60,11 @@ def _sharpen(img8: np.ndarray) -> np.ndarray:
 def main(argv=None) -> int:
     argv = list(sys.argv[1:] if argv is None else argv)
     n_override = None
+    radius = None
+    if "--radius" in argv:
+        i = argv.index("--radius")
+        radius = int(argv[i + 1])
+        del argv[i:i + 2]
     if "--frames" in argv:
         i = argv.index("--frames")
         n_override = int(argv[i + 1])
@@ -107,16 +115,29 @@ def main(argv=None) -> int:
     p.merge_flags = 1                         # GammasRGB: the result is written as an 8-bit image
     while p.levels > 1 and min(h, w) >> (p.levels - 1) < 2 * p.max_shift + p.tile_size:
         p.levels -= 1
-    sr = BurstSuperResolution(p, device=0, max_width=w, max_height=h, max_frames=n)
-    dev = torch.from_numpy(raw.view(np.int16)).cuda()
     num_times, real_times = 10, 5
+    sr = BurstSuperResolution(p, device=0, max_width=w, max_height=h, max_frames=n if radius is None else 2 * radius + 1)
+    dev = torch.from_numpy(raw.view(np.int16)).cuda()
     out = None
-    for t in range(num_times):
-        if t == num_times - real_times:
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-        sr.set_input(dev)
-        out = sr.next_frame()
+    if radius is None:
+        for t in range(num_times):
+            if t == num_times - real_times:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            sr.set_input(dev)
+            out = sr.next_frame()
+    else:
+        sr.set_temporal_area_radius(radius)
+        sr.set_input(dev.repeat(num_times, 1, 1))             # :168-176: the frame set, num_times over
+        start_i = (num_times - real_times) * n
+        for i in range(n * num_times):
+            if i == start_i:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            res = sr.next_frame()
+            if res is None:                                   # :191 result.empty()
+                break
+            out = res
     torch.cuda.synchronize()
     sec = time.perf_counter() - t0
     print(f"{sec:.6g} sec")

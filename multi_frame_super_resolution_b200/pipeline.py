@@ -2,9 +2,18 @@
 
 The reference's only runnable burst program drives `cv::superres::SuperResolution`
 (finalProject/Project/multi_frame_sr.cpp:165-194): create, setScale / setIterations /
-setInput, then pull the result with nextFrame().  `BurstSuperResolution` keeps that shape
-(set_scale, set_iterations, set_input, next_frame) on top of mfsr_create / mfsr_set_frames /
-mfsr_run.  All arithmetic happens in libmfsr_b200.so; there is no CPU fallback.
+setTemporalAreaRadius / setInput, then pull results with nextFrame().  `BurstSuperResolution`
+keeps that shape (set_scale, set_iterations, set_temporal_area_radius, set_input, next_frame) on
+top of mfsr_create / mfsr_set_frames / mfsr_run.  Two pull modes:
+
+* whole burst (default): set_input(frames) is one burst, next_frame() merges all of it onto
+  frame `ref_idx` (BASELINE configs);
+* temporal area (multi_frame_sr.cpp:182 setTemporalAreaRadius(1), :185-194 the nextFrame loop):
+  set_input(frames) is a frame SEQUENCE, each next_frame() returns the super-resolved frame i
+  merged from frames [i - r, i + r] (clipped at the ends of the sequence) and advances i;
+  None once the sequence is exhausted (the reference's empty result, :191).
+
+All arithmetic happens in libmfsr_b200.so; there is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -66,6 +75,10 @@ class BurstSuperResolution:
         self._shape = None
         self._n = 0
         self._keep = None
+        self._keep_ev = None
+        self._radius = None          # None: whole-burst mode
+        self._seq = None             # temporal-area mode: (frames, fmt), position
+        self._pos = 0
 
     # -- cv::superres-style setters (multi_frame_sr.cpp:179-182); take effect at the next (re)create
     def set_scale(self, scale: int):
@@ -76,6 +89,19 @@ class BurstSuperResolution:
         """Reference: BTV-L1 iterations; here: Lucas-Kanade refinement sweeps."""
         self._destroy()
         self.params.lk_iterations = int(iterations)
+
+    def set_temporal_area_radius(self, radius: Optional[int]):
+        """multi_frame_sr.cpp:182.  radius >= 0 switches to the sliding mode (one output per input frame, window 2 r + 1);
+        None goes back to whole-burst mode.  Takes effect at the next set_input()."""
+        if radius is not None and radius < 0:
+            raise ValueError("temporal area radius must be >= 0 (None = whole burst)")
+        self._radius = None if radius is None else int(radius)
+        self._seq = None
+        self._shape = None
+
+    def reset(self):
+        """Rewind the frame sequence (FrameSource::reset, multi_frame_sr.cpp:46-49)."""
+        self._pos = 0
 
     def _ensure(self):
         if not self._h:
@@ -118,6 +144,17 @@ class BurstSuperResolution:
 
     # -- setInput: frames is a CUDA tensor [N,H,W] (uint16/int16) or a host numpy/pinned tensor of the same shape
     def set_input(self, frames, ref_idx: int = 0, fmt: int = FMT_BAYER_U16):
+        if self._radius is not None:
+            if 2 * self._radius + 1 > self._max[2]:
+                raise ValueError(f"temporal area 2*{self._radius}+1 exceeds max_frames={self._max[2]}")
+            if len(frames.shape) != 3:
+                raise ValueError("frames must be [N,H,W]")
+            self._seq, self._pos = (frames, fmt), 0
+            self._shape = tuple(frames.shape[1:])
+            return
+        self._set_window(frames, ref_idx, fmt)
+
+    def _set_window(self, frames, ref_idx: int, fmt: int):
         self._ensure()
         if isinstance(frames, np.ndarray):
             if frames.dtype != np.uint16 or frames.ndim != 3 or not frames.flags.c_contiguous:
@@ -133,10 +170,21 @@ class BurstSuperResolution:
             # the frames were produced on torch's current stream: order the handle's stream after it
             self._ext().wait_stream(torch.cuda.current_stream(self.device))
         ptrs = (C.c_void_p * n)(*[base + i * h * w * 2 for i in range(n)])
+        old = self._keep
+        if isinstance(old, torch.Tensor) and old.is_cuda:
+            # device frames are read in place until the end of the run: their memory must not be handed out again by the
+            # caching allocator before the handle's stream has passed that work
+            old.record_stream(self._ext())
+        elif old is not None and self._keep_ev is not None:
+            self._keep_ev.synchronize()      # host source of the async H2D copies: wait for the copies (not for the run)
         check(self._lib.mfsr_set_frames(self._h, ptrs, n, w, h, w * 2, fmt, ref_idx, on_host), "mfsr_set_frames")
         self._shape = (h, w)
         self._n = n
         self._keep = frames          # the async H2D copies read it until the stream reaches them
+        self._keep_ev = None
+        if on_host:
+            self._keep_ev = torch.cuda.Event()
+            self._keep_ev.record(self._ext())
 
     # -- nextFrame: run the whole chain, return the float3 image
     def next_frame(self, out=None, host: bool = False, sync: bool = True, dtype: torch.dtype = torch.float32):
@@ -144,7 +192,18 @@ class BurstSuperResolution:
         dtype: torch.float32 (mfsr_run), torch.float16 or torch.uint8 (mfsr_run_format: half3 / 8-bit image)."""
         if self._shape is None:
             raise RuntimeError("set_input() first")
+        if self._radius is not None:
+            frames, fmt = self._seq
+            n, i, r = frames.shape[0], self._pos, self._radius
+            if i >= n:
+                return None
+            lo, hi = max(0, i - r), min(n, i + r + 1)
+            self._set_window(frames[lo:hi], i - lo, fmt)
+            self._pos = i + 1
         ow, oh = self.output_size(self._shape[1], self._shape[0])
+        if out is not None and isinstance(out, torch.Tensor) and out.is_cuda:
+            # a consumer on torch's current stream may still be reading the previous result from `out`
+            self._ext().wait_stream(torch.cuda.current_stream(self.device))
         if dtype != torch.float32:
             fmt = {torch.float16: OUT_F16, torch.uint8: OUT_U8}[dtype]
             if out is None:

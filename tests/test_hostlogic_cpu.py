@@ -70,3 +70,21 @@ def test_band_params_fields():
     # stencils 27 rows + the aligner's reach 4 * (2^4 - 1) = 60 rows, rounded up to the LK tile height
     assert rowband.default_margin(p) == 96
     assert p.band_global_h == 0 and rowband.band_params(p, bands[0], 6048, margin=0).band_margin == 0     # the input params are not modified
+
+
+def test_temporal_area_setters_validate_without_gpu():
+    """multi_frame_sr.cpp:182 setTemporalAreaRadius: the setter and the sequence bookkeeping are host logic."""
+    import pytest
+    from multi_frame_super_resolution_b200.pipeline import BurstSuperResolution
+    sr = BurstSuperResolution(default_params(), max_width=64, max_height=64, max_frames=3)
+    with pytest.raises(ValueError):
+        sr.set_temporal_area_radius(-1)
+    sr.set_temporal_area_radius(2)
+    with pytest.raises(ValueError):
+        sr.set_input(np.zeros((6, 64, 64), np.uint16))          # window 5 > max_frames 3
+    sr.set_temporal_area_radius(1)
+    sr.set_input(np.zeros((6, 64, 64), np.uint16))              # no device work before the first next_frame()
+    assert sr._pos == 0 and sr._shape == (64, 64)
+    sr.set_temporal_area_radius(None)
+    with pytest.raises(RuntimeError):
+        sr.next_frame()                                         # whole-burst mode again: needs set_input first
