@@ -50,6 +50,19 @@ __device__ __forceinline__ T* row_ptr(T* base, int64_t pitch_bytes, int y)
     return (T*)((char*)base + pitch_bytes * (int64_t)y);
 }
 
+// Kernels that run once per frame take the frame from blockIdx.z: one launch per burst instead of one per frame.
+template <typename T>
+__device__ __forceinline__ T* frame_ptr(T* base, int64_t frame_stride_bytes, unsigned frame)
+{
+    return (T*)((char*)base + frame_stride_bytes * (int64_t)frame);
+}
+template <typename T>
+__device__ __forceinline__ const T* frame_ptr(const T* base, int64_t frame_stride_bytes, unsigned frame)
+{
+    return (const T*)((const char*)base + frame_stride_bytes * (int64_t)frame);
+}
+struct FrameStrides { int64_t s[3]; };
+
 // ---- texture model (linear filter, clamp address, 1.8 fixed-point fraction) ----
 // Models the cudaTextureObject_t fetches of the reference (e.g.
 // DeBayerKernels.cu:401-402, opticalFlow.cu:36-41,88, RobustnessModell.cu:58)

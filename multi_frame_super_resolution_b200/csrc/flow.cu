@@ -18,9 +18,11 @@ constexpr int FFT_ROWS = 8;      // rows per thread: the column-only part (textu
 __global__ void __launch_bounds__(256)
 flow_from_tiles_kernel(const float2* __restrict__ tiles, int64_t tile_pitch, int tilesX, int tilesY,
                        float2* __restrict__ flow, int64_t flow_pitch, int w, int h, float bsx, float bsy, float cr, float sr,
-                       int gh, int gy0, int gty, int trow0, const float* __restrict__ frame_pose)
+                       int gh, int gy0, int gty, int trow0, const float* __restrict__ frame_pose, int64_t tiles_fs, int64_t flow_fs)
 {
-    if (frame_pose) { bsx = frame_pose[0]; bsy = frame_pose[1]; cr = frame_pose[2]; sr = frame_pose[3]; }      // prealign.cu
+    tiles = frame_ptr(tiles, tiles_fs, blockIdx.z);      // blockIdx.z = frame
+    flow = frame_ptr(flow, flow_fs, blockIdx.z);
+    if (frame_pose) { frame_pose += 4 * blockIdx.z; bsx = frame_pose[0]; bsy = frame_pose[1]; cr = frame_pose[2]; sr = frame_pose[3]; }      // prealign.cu
     const int x = blockIdx.x * blockDim.x + threadIdx.x, yb = (blockIdx.y * blockDim.y + threadIdx.y) * FFT_ROWS;
     if (x >= w || yb >= h) return;
     const float bx = cr * -bsx - sr * -bsy, by = sr * -bsx + cr * -bsy;
@@ -107,9 +109,20 @@ template <int HW, int MODE>
 __global__ void __launch_bounds__(256, 4)
 lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov, int64_t img_pitch,
                     const float2* __restrict__ flow_in, float2* __restrict__ flow_out, int64_t flow_pitch,
-                    int w, int h, float minDet, int gh, int gy0, cudaTextureObject_t movtex)
+                    int w, int h, float minDet, int gh, int gy0, cudaTextureObject_t movtex, int64_t mov_fs, int64_t flow_fs, int ref_frame)
 {
     constexpr bool BAND = MODE == 1;
+    // blockIdx.z = frame.  The reference frame against itself has Iz == 0, hence UV == 0: its flow is copied.
+    mov = frame_ptr(mov, mov_fs, blockIdx.z);
+    flow_in = frame_ptr(flow_in, flow_fs, blockIdx.z);
+    flow_out = frame_ptr(flow_out, flow_fs, blockIdx.z);
+    if ((int)blockIdx.z == ref_frame) {
+        const int gx = blockIdx.x * LTW + threadIdx.x;
+        if (gx < w)
+            for (int gy = blockIdx.y * LTH + threadIdx.y; gy < min((int)(blockIdx.y + 1) * LTH, h); gy += blockDim.y)
+                row_ptr(flow_out, flow_pitch, gy)[gx] = __ldg(row_ptr(flow_in, flow_pitch, gy) + gx);
+        return;
+    }
     // gh / gy0: height of the full frame and global row of local row 0 (row-band mode; gh == h, gy0 == 0 otherwise): the warp's
     // texture coordinates are normalised by the FULL frame so that a band reproduces the full-frame arithmetic bit for bit
     constexpr int RW = LTW + 2 * HW, RH = LTH + 2 * HW;       // derivative region
@@ -302,13 +315,16 @@ lk_iteration_kernel(const float* __restrict__ ref, const float* __restrict__ mov
 
 using namespace mfsr;
 
+// frames > 1: frame f reads tiles + f * tiles_fs (bytes) and frame_pose + 4 f, writes flow + f * flow_fs
 int mfsr::launch_flow_from_tiles(const float2* tiles, int64_t tile_pitch, int tilesX, int tilesY, float2* flow, int64_t flow_pitch, int w, int h,
-                                 float bsx, float bsy, float rot, int gh, int gy0, int gty, int tile_row0, cudaStream_t st, const float* frame_pose)
+                                 float bsx, float bsy, float rot, int gh, int gy0, int gty, int tile_row0, cudaStream_t st, const float* frame_pose,
+                                 int frames, int64_t tiles_fs, int64_t flow_fs)
 {
-    if (!tiles || !flow || tilesX < 1 || tilesY < 1 || w < 1 || h < 1) return MFSR_E_INVALID;
+    if (!tiles || !flow || tilesX < 1 || tilesY < 1 || w < 1 || h < 1 || frames < 1) return MFSR_E_INVALID;
     if (gh <= 0) { gh = h; gy0 = 0; gty = tilesY; tile_row0 = 0; }
-    dim3 b(32, 8), g(cdiv(w, 32), cdiv(h, 8 * FFT_ROWS));
-    flow_from_tiles_kernel<<<g, b, 0, st>>>(tiles, tile_pitch, tilesX, tilesY, flow, flow_pitch, w, h, bsx, bsy, cosf(rot), sinf(rot), gh, gy0, gty, tile_row0, frame_pose);
+    dim3 b(32, 8), g(cdiv(w, 32), cdiv(h, 8 * FFT_ROWS), frames);
+    flow_from_tiles_kernel<<<g, b, 0, st>>>(tiles, tile_pitch, tilesX, tilesY, flow, flow_pitch, w, h, bsx, bsy, cosf(rot), sinf(rot), gh, gy0, gty, tile_row0, frame_pose,
+                                            tiles_fs, flow_fs);
     MFSR_LAUNCH_CHECK();
     return MFSR_OK;
 }
@@ -322,20 +338,25 @@ extern "C" int mfsr_stage_flow_from_tiles(const float* tile_shift, int64_t tile_
                                   base_shift_x, base_shift_y, base_rotation, 0, 0, 0, 0, (cudaStream_t)stream);
 }
 
+// frames > 1: one sweep for every frame of the burst (frame f: mov + f * mov_fs, flow + f * flow_fs; frame `ref_frame`, if >= 0, is the
+// reference frame itself and only has its flow copied).  The texture form is per frame (one texture object per moved image).
 int mfsr::launch_lk_iteration(const float* ref, const float* mov, int64_t img_pitch, const float2* flow_in, float2* flow_out, int64_t flow_pitch,
-                              int width, int height, int half_window, float min_det, int gh, int gy0, cudaStream_t st, cudaTextureObject_t movtex)
+                              int width, int height, int half_window, float min_det, int gh, int gy0, cudaStream_t st, cudaTextureObject_t movtex,
+                              int frames, int64_t mov_fs, int64_t flow_fs, int ref_frame)
 {
-    if (!ref || !mov || !flow_in || !flow_out || flow_in == flow_out || width < 1 || height < 1) return MFSR_E_INVALID;
+    if (!ref || !mov || !flow_in || !flow_out || flow_in == flow_out || width < 1 || height < 1 || frames < 1) return MFSR_E_INVALID;
+    if (movtex && frames != 1) return MFSR_E_INVALID;
     if (half_window < 1 || half_window > LHW_MAX) return MFSR_E_INVALID;
     // 32-bit element indexing inside the kernel
     if ((img_pitch & 3) || (flow_pitch & 7) || (int64_t)(img_pitch >> 2) * height >= (1ll << 31) || (int64_t)(flow_pitch >> 3) * height >= (1ll << 31)) return MFSR_E_INVALID;
     if (gh <= 0) { gh = height; gy0 = 0; }
-    dim3 b(LTW, 8), g(cdiv(width, LTW), cdiv(height, LTH));
+    dim3 b(LTW, 8), g(cdiv(width, LTW), cdiv(height, LTH), frames);
     const bool band = !(gh == height && gy0 == 0);
     if (band) movtex = 0;             // a band reproduces the full frame bit for bit only with the ALU model (texture rows of the full frame)
-#define MFSR_LK(HW_) do { if (band) lk_iteration_kernel<HW_, 1><<<g, b, 0, st>>>(ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0, 0); \
-                          else if (movtex) lk_iteration_kernel<HW_, 2><<<g, b, 0, st>>>(ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0, movtex); \
-                          else lk_iteration_kernel<HW_, 0><<<g, b, 0, st>>>(ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0, 0); } while (0)
+#define MFSR_LK_ARGS ref, mov, img_pitch, flow_in, flow_out, flow_pitch, width, height, min_det, gh, gy0
+#define MFSR_LK(HW_) do { if (band) lk_iteration_kernel<HW_, 1><<<g, b, 0, st>>>(MFSR_LK_ARGS, 0, mov_fs, flow_fs, ref_frame); \
+                          else if (movtex) lk_iteration_kernel<HW_, 2><<<g, b, 0, st>>>(MFSR_LK_ARGS, movtex, mov_fs, flow_fs, ref_frame); \
+                          else lk_iteration_kernel<HW_, 0><<<g, b, 0, st>>>(MFSR_LK_ARGS, 0, mov_fs, flow_fs, ref_frame); } while (0)
     switch (half_window) {
         case 1: MFSR_LK(1); break;
         case 2: MFSR_LK(2); break;
@@ -343,6 +364,7 @@ int mfsr::launch_lk_iteration(const float* ref, const float* mov, int64_t img_pi
         default: MFSR_LK(4); break;
     }
 #undef MFSR_LK
+#undef MFSR_LK_ARGS
     MFSR_LAUNCH_CHECK();
     return MFSR_OK;
 }

@@ -11,14 +11,17 @@
 // instead of a second launch reading the first one's HBM output — and the absent
 // host's B/W + Gaussian (gaussin_filter_1D, main.cpp:370) + resize steps.
 #include "common.cuh"
+#include "internal.h"
 
 namespace mfsr {
 
 // ---------------------------------------------------------------- subsample3
 __global__ void __launch_bounds__(256)
 subsample3_kernel(const uint16_t* __restrict__ raw, int64_t raw_pitch, float* __restrict__ out, int64_t out_pitch,
-                  float factor, int dimX, int dimY, Cfa cfa)
+                  float factor, int dimX, int dimY, Cfa cfa, int64_t raw_fs, int64_t out_fs)
 {
+    raw = frame_ptr(raw, raw_fs, blockIdx.z);       // one launch per burst: blockIdx.z = frame
+    out = frame_ptr(out, out_fs, blockIdx.z);
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= dimX || y >= dimY) return;
@@ -166,8 +169,11 @@ struct Taps { float t[MAX_TAPS]; int n; };
 template <int R, bool PN>
 __global__ void __launch_bounds__(256)
 tracking_kernel(const uint16_t* __restrict__ raw, int64_t raw_pitch, float* __restrict__ gray, int64_t gray_pitch,
-                uint8_t* __restrict__ gray_q, int64_t gq_pitch, int w, int h, Cfa cfa, F3 black, F3 scale, Taps taps, float qmax)
+                uint8_t* __restrict__ gray_q, int64_t gq_pitch, int w, int h, Cfa cfa, F3 black, F3 scale, Taps taps, float qmax, FrameStrides fs)
 {
+    raw = frame_ptr(raw, fs.s[0], blockIdx.z);
+    if (gray) gray = frame_ptr(gray, fs.s[1], blockIdx.z);
+    if (gray_q) gray_q = frame_ptr(gray_q, fs.s[2], blockIdx.z);
     constexpr int TW = 64, TH = (R <= 2) ? 32 : 16;
     constexpr int LW = TW + 2 * R, LH = TH + 2 * R;
     __shared__ DemosaicTile<TW, TH, R> S;
@@ -264,8 +270,11 @@ __device__ __forceinline__ float px_green(const float* __restrict__ rw)
 template <int R, int PAT>
 __global__ void __launch_bounds__(256)
 tracking_quad_kernel(const uint16_t* __restrict__ raw, int64_t raw_pitch, float* __restrict__ gray, int64_t gray_pitch,
-                     uint8_t* __restrict__ gray_q, int64_t gq_pitch, int w, int h, F3 black, F3 scale, Taps taps, float qmax)
+                     uint8_t* __restrict__ gray_q, int64_t gq_pitch, int w, int h, F3 black, F3 scale, Taps taps, float qmax, FrameStrides fs)
 {
+    raw = frame_ptr(raw, fs.s[0], blockIdx.z);
+    if (gray) gray = frame_ptr(gray, fs.s[1], blockIdx.z);
+    if (gray_q) gray_q = frame_ptr(gray_q, fs.s[2], blockIdx.z);
     constexpr int TW = 64, TH = 32;
     constexpr int RW = TW + 2 * (R + 3), RH = TH + 2 * (R + 3);      // normalised raw plane, origin (x0 - R - 3, y0 - R - 3)
     constexpr int GW = TW + 2 * (R + 1), GH = TH + 2 * (R + 1);      // green plane,          origin (x0 - R - 1, y0 - R - 1)
@@ -396,8 +405,11 @@ tracking_quad_kernel(const uint16_t* __restrict__ raw, int64_t raw_pitch, float*
 
 // ---------------------------------------------------------------- pyramid
 __global__ void __launch_bounds__(256)
-pyramid_down_kernel(const uint8_t* __restrict__ in, int64_t in_pitch, uint8_t* __restrict__ out, int64_t out_pitch, int ow, int oh)
+pyramid_down_kernel(const uint8_t* __restrict__ in, int64_t in_pitch, uint8_t* __restrict__ out, int64_t out_pitch, int ow, int oh,
+                    int64_t in_fs, int64_t out_fs)
 {
+    in = frame_ptr(in, in_fs, blockIdx.z);
+    out = frame_ptr(out, out_fs, blockIdx.z);
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= ow || y >= oh) return;
     const uint8_t* r0 = row_ptr(in, in_pitch, 2 * y) + 2 * x;
@@ -453,14 +465,20 @@ using namespace mfsr;
 static Cfa mk_cfa(const int cfa[4]) { Cfa c; for (int i = 0; i < 4; i++) c.c[i] = cfa[i]; return c; }
 static F3 mk_f3(const float v[3]) { F3 f; for (int i = 0; i < 3; i++) f.v[i] = v[i]; return f; }
 
+int mfsr::launch_subsample3(const uint16_t* raw, int64_t raw_pitch, int64_t raw_fs, float* rgb_half, int64_t rgb_pitch, int64_t rgb_fs, int frames,
+                      float maxVal, int dimX, int dimY, const int cfa[4], cudaStream_t stream)
+{
+    if (!raw || !rgb_half || !cfa || dimX <= 0 || dimY <= 0 || frames < 1 || ((raw_pitch | raw_fs) & 3) || ((uintptr_t)raw & 3)) return MFSR_E_INVALID;
+    dim3 b(32, 8), g(cdiv(dimX, 32), cdiv(dimY, 8), frames);
+    subsample3_kernel<<<g, b, 0, stream>>>(raw, raw_pitch, rgb_half, rgb_pitch, 1.0f / maxVal, dimX, dimY, mk_cfa(cfa), raw_fs, rgb_fs);
+    MFSR_LAUNCH_CHECK();
+    return MFSR_OK;
+}
+
 extern "C" int mfsr_stage_subsample3(const uint16_t* raw, int64_t raw_pitch, float* rgb_half, int64_t rgb_pitch,
                                      float maxVal, int dimX, int dimY, const int cfa[4], void* stream)
 {
-    if (!raw || !rgb_half || !cfa || dimX <= 0 || dimY <= 0 || (raw_pitch & 3) || ((uintptr_t)raw & 3)) return MFSR_E_INVALID;
-    dim3 b(32, 8), g(cdiv(dimX, 32), cdiv(dimY, 8));
-    subsample3_kernel<<<g, b, 0, (cudaStream_t)stream>>>(raw, raw_pitch, rgb_half, rgb_pitch, 1.0f / maxVal, dimX, dimY, mk_cfa(cfa));
-    MFSR_LAUNCH_CHECK();
-    return MFSR_OK;
+    return launch_subsample3(raw, raw_pitch, 0, rgb_half, rgb_pitch, 0, 1, maxVal, dimX, dimY, cfa, (cudaStream_t)stream);
 }
 
 extern "C" int mfsr_stage_demosaic(const uint16_t* raw, int64_t raw_pitch, float* rgb, int64_t rgb_pitch,
@@ -473,11 +491,13 @@ extern "C" int mfsr_stage_demosaic(const uint16_t* raw, int64_t raw_pitch, float
     return MFSR_OK;
 }
 
-extern "C" int mfsr_stage_tracking_image(const uint16_t* raw, int64_t raw_pitch, float* gray, int64_t gray_pitch,
-                                         uint8_t* gray_q, int64_t gray_q_pitch, int width, int height, const int cfa[4],
-                                         const float black[3], const float scale[3], float sigma, int track_bits, void* stream)
+int mfsr::launch_tracking_image(const uint16_t* raw, int64_t raw_pitch, int64_t raw_fs, float* gray, int64_t gray_pitch, int64_t gray_fs,
+                          uint8_t* gray_q, int64_t gray_q_pitch, int64_t gray_q_fs, int frames, int width, int height, const int cfa[4],
+                          const float black[3], const float scale[3], float sigma, int track_bits, cudaStream_t stream)
 {
-    if (!raw || !cfa || !black || !scale || width <= 0 || height <= 0 || track_bits < 1 || track_bits > 8) return MFSR_E_INVALID;
+    if (!raw || !cfa || !black || !scale || width <= 0 || height <= 0 || frames < 1 || track_bits < 1 || track_bits > 8) return MFSR_E_INVALID;
+    FrameStrides fs;
+    fs.s[0] = raw_fs; fs.s[1] = gray_fs; fs.s[2] = gray_q_fs;
     Taps t;
     t.n = gauss_taps(sigma, t.t);
     if (t.n < 0) return MFSR_E_INVALID;
@@ -493,8 +513,8 @@ extern "C" int mfsr_stage_tracking_image(const uint16_t* raw, int64_t raw_pitch,
     if (R < 1 || R > 4) return MFSR_E_INVALID;
     if (pn && R <= 2) {
         const int pat = cfa[0] | (cfa[1] << 2) | (cfa[2] << 4) | (cfa[3] << 6);
-        dim3 bq(64, 4), gq(cdiv(width, 64), cdiv(height, 32));
-#define MFSR_TQ(RR, PP) tracking_quad_kernel<RR, PP><<<gq, bq, 0, st>>>(raw, raw_pitch, gray, gray_pitch, gray_q, gray_q_pitch, width, height, bl, sc, t, qmax)
+        dim3 bq(64, 4), gq(cdiv(width, 64), cdiv(height, 32), frames);
+#define MFSR_TQ(RR, PP) tracking_quad_kernel<RR, PP><<<gq, bq, 0, st>>>(raw, raw_pitch, gray, gray_pitch, gray_q, gray_q_pitch, width, height, bl, sc, t, qmax, fs)
 #define MFSR_TQP(PP) if (pat == (PP)) { if (R == 1) MFSR_TQ(1, PP); else MFSR_TQ(2, PP); MFSR_LAUNCH_CHECK(); return MFSR_OK; }
         MFSR_TQP(0 | (1 << 2) | (1 << 4) | (2 << 6))      // RGGB
         MFSR_TQP(2 | (1 << 2) | (1 << 4) | (0 << 6))      // BGGR
@@ -504,8 +524,8 @@ extern "C" int mfsr_stage_tracking_image(const uint16_t* raw, int64_t raw_pitch,
 #undef MFSR_TQP
 #undef MFSR_TQ
     }
-    dim3 b(64, 4), g(cdiv(width, 64), cdiv(height, R <= 2 ? 32 : 16));
-#define MFSR_TRK(RR, PP) tracking_kernel<RR, PP><<<g, b, 0, st>>>(raw, raw_pitch, gray, gray_pitch, gray_q, gray_q_pitch, width, height, c, bl, sc, t, qmax)
+    dim3 b(64, 4), g(cdiv(width, 64), cdiv(height, R <= 2 ? 32 : 16), frames);
+#define MFSR_TRK(RR, PP) tracking_kernel<RR, PP><<<g, b, 0, st>>>(raw, raw_pitch, gray, gray_pitch, gray_q, gray_q_pitch, width, height, c, bl, sc, t, qmax, fs)
     switch (R * 2 + (pn ? 1 : 0)) {
         case 2: MFSR_TRK(1, false); break;  case 3: MFSR_TRK(1, true); break;
         case 4: MFSR_TRK(2, false); break;  case 5: MFSR_TRK(2, true); break;
@@ -517,14 +537,28 @@ extern "C" int mfsr_stage_tracking_image(const uint16_t* raw, int64_t raw_pitch,
     return MFSR_OK;
 }
 
-extern "C" int mfsr_stage_pyramid_down(const uint8_t* in, int64_t in_pitch, int in_w, int in_h, uint8_t* out, int64_t out_pitch, void* stream)
+extern "C" int mfsr_stage_tracking_image(const uint16_t* raw, int64_t raw_pitch, float* gray, int64_t gray_pitch,
+                                         uint8_t* gray_q, int64_t gray_q_pitch, int width, int height, const int cfa[4],
+                                         const float black[3], const float scale[3], float sigma, int track_bits, void* stream)
 {
-    if (!in || !out || in_w < 2 || in_h < 2) return MFSR_E_INVALID;
+    return launch_tracking_image(raw, raw_pitch, 0, gray, gray_pitch, 0, gray_q, gray_q_pitch, 0, 1, width, height, cfa, black, scale, sigma, track_bits,
+                                 (cudaStream_t)stream);
+}
+
+int mfsr::launch_pyramid_down(const uint8_t* in, int64_t in_pitch, int64_t in_fs, int in_w, int in_h, uint8_t* out, int64_t out_pitch, int64_t out_fs, int frames,
+                        cudaStream_t stream)
+{
+    if (!in || !out || in_w < 2 || in_h < 2 || frames < 1) return MFSR_E_INVALID;
     const int ow = in_w / 2, oh = in_h / 2;
-    dim3 b(32, 8), g(cdiv(ow, 32), cdiv(oh, 8));
-    pyramid_down_kernel<<<g, b, 0, (cudaStream_t)stream>>>(in, in_pitch, out, out_pitch, ow, oh);
+    dim3 b(32, 8), g(cdiv(ow, 32), cdiv(oh, 8), frames);
+    pyramid_down_kernel<<<g, b, 0, stream>>>(in, in_pitch, out, out_pitch, ow, oh, in_fs, out_fs);
     MFSR_LAUNCH_CHECK();
     return MFSR_OK;
+}
+
+extern "C" int mfsr_stage_pyramid_down(const uint8_t* in, int64_t in_pitch, int in_w, int in_h, uint8_t* out, int64_t out_pitch, void* stream)
+{
+    return launch_pyramid_down(in, in_pitch, 0, in_w, in_h, out, out_pitch, 0, 1, (cudaStream_t)stream);
 }
 
 extern "C" int mfsr_stage_fallback_upsample(const float* rgb, int64_t rgb_pitch, int width, int height,

@@ -43,7 +43,20 @@ int launch_consolidate(const float2* measured, int64_t tile_stride, int64_t pair
 // gy0 / T) so that a band reproduces the full-frame flow.  gh == 0: plain local mapping.
 int launch_flow_from_tiles(const float2* tiles, int64_t tile_pitch, int tilesX, int tilesY, float2* flow, int64_t flow_pitch, int w, int h,
                            float bsx, float bsy, float rot, int gh, int gy0, int gty, int tile_row0, cudaStream_t st,
-                           const float* frame_pose = nullptr);      // frame_pose: device (bx, by, cos, sin) replacing bsx / bsy / rot
+                           const float* frame_pose = nullptr,      // frame_pose: device (bx, by, cos, sin) replacing bsx / bsy / rot
+                           int frames = 1, int64_t tiles_fs = 0, int64_t flow_fs = 0);      // one launch for `frames` frames (strides in bytes)
+
+// per-frame kernels launched once per burst (grid.z = frame, frame strides in bytes)
+int launch_subsample3(const uint16_t* raw, int64_t raw_pitch, int64_t raw_fs, float* rgb_half, int64_t rgb_pitch, int64_t rgb_fs, int frames,
+                      float maxVal, int dimX, int dimY, const int cfa[4], cudaStream_t stream);
+int launch_tracking_image(const uint16_t* raw, int64_t raw_pitch, int64_t raw_fs, float* gray, int64_t gray_pitch, int64_t gray_fs,
+                          uint8_t* gray_q, int64_t gray_q_pitch, int64_t gray_q_fs, int frames, int width, int height, const int cfa[4],
+                          const float black[3], const float scale[3], float sigma, int track_bits, cudaStream_t stream);
+int launch_pyramid_down(const uint8_t* in, int64_t in_pitch, int64_t in_fs, int in_w, int in_h, uint8_t* out, int64_t out_pitch, int64_t out_fs, int frames,
+                        cudaStream_t stream);
+int launch_robustness(const float* rgb_ref, const float* rgb_mov, int64_t rgb_pitch, int64_t rgb_fs, const float* flow, int64_t flow_pitch,
+                      int64_t flow_fs, float* mask, int64_t mask_pitch, int64_t mask_fs, float* scratch, int64_t scratch_fs, int frames,
+                      int w, int h, float alpha, float beta, float thresholdM, int erode_radius, cudaStream_t st);
 
 // global pre-alignment (prealign.cu)
 int launch_prealign_stage(const uint8_t* img, int64_t pitch, int64_t frame_stride, int w, int h, int n_frames, int ref_idx,
@@ -55,7 +68,8 @@ int launch_pair_pose(const float* pose, const PairTable& pt, int m, float* pair_
 
 // one Lucas-Kanade sweep; gh / gy0 as above (0: whole frame)
 int launch_lk_iteration(const float* ref, const float* mov, int64_t img_pitch, const float2* flow_in, float2* flow_out, int64_t flow_pitch,
-                        int width, int height, int half_window, float min_det, int gh, int gy0, cudaStream_t st, cudaTextureObject_t movtex = 0);
+                        int width, int height, int half_window, float min_det, int gh, int gy0, cudaStream_t st, cudaTextureObject_t movtex = 0,
+                        int frames = 1, int64_t mov_fs = 0, int64_t flow_fs = 0, int ref_frame = -1);
 // movtex != 0 (and not a band): the warp step samples the moved image through this texture (make_gray_texture) instead of the ALU model
 int make_gray_texture(const float* img, int64_t pitch, int width, int height, cudaTextureObject_t* out);
 

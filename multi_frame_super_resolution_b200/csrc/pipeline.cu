@@ -51,7 +51,7 @@ struct mfsr_context {
     float* gray; int64_t gray_pitch, gray_fs;
     float* rgb_ref; int64_t rgb_pitch;
     float2* flowA; float2* flowB; int64_t flow_pitch, flow_fs;
-    float4* mask; float4* mask_tmp; int64_t mask_pitch, mask_fs;
+    float4* mask; float4* mask_tmp; int64_t mask_pitch, mask_fs, mask_tmp_cap; int mask_chunk;
     float4* kern; int64_t kern_pitch;
     float* fallback; float* outbuf; int64_t out_pitch_own;
     float* part_sum; float* part_weight;               // partial sums of the frame-chunked merge (bursts of more than 10 frames), else null
@@ -209,7 +209,10 @@ static size_t carve(mfsr_context* c, char* base, int n, int w, int h)
     c->flowB = (float2*)take((size_t)c->flow_fs * n);
     c->mask_pitch = (int64_t)hw * 16; c->mask_fs = c->mask_pitch * hh;
     c->mask = (float4*)take((size_t)c->mask_fs * n);
-    c->mask_tmp = (float4*)take((size_t)c->mask_fs);
+    // scratch of the min filter: as many frames as fit in about half of the L2 (at least one)
+    if (!base) c->mask_tmp_cap = c->mask_fs * std::min<int64_t>(n, std::max<int64_t>(1, (48ll << 20) / c->mask_fs));      // sized at create
+    c->mask_chunk = (int)std::min<int64_t>(n, std::max<int64_t>(1, c->mask_tmp_cap / c->mask_fs));
+    c->mask_tmp = (float4*)take((size_t)c->mask_fs * c->mask_chunk);
     c->kern_pitch = (int64_t)w * 16;
     c->kern = (float4*)take((size_t)c->kern_pitch * h);
     mfsr_merge_geom g; make_geom(p, w, h, &g);
@@ -346,7 +349,7 @@ extern "C" int mfsr_set_frames(mfsr_handle h, const void* const* frames, int n, 
     if (build_pairs(h->p, n, ref_idx, nullptr, nullptr, 0) > CONS_MAX_M) return MFSR_E_INVALID;
     h->have_frames = false; h->ran = false;
     MFSR_CUDA_TRY(cudaSetDevice(h->device));
-    carve(h, h->ws, n, width, height);
+    if (carve(h, h->ws, n, width, height) > h->ws_bytes) return MFSR_E_INVALID;      // cannot happen for n, width, height within the handle's maxima
     if (h->lv.empty()) return MFSR_E_INVALID;
     h->n = n; h->w = width; h->h = height; h->ref_idx = ref_idx; h->format = format;
     make_geom(h->p, width, height, &h->geom);
@@ -433,16 +436,13 @@ static int run_impl(mfsr_handle h, void* out_any, int64_t out_pitch, int out_on_
     // ---- A. front end: half-res RGB, tracking gray (float + 7-bit), pyramid, demosaiced reference
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_FRONTEND], st));
     const float maxVal = p.white_level[1] + p.black_level[1];
-    for (int f = 0; f < n; f++) {
-        const uint16_t* raw = (const uint16_t*)((const char*)h->rawp + h->rawp_fs * f);
-        RUN(mfsr_stage_subsample3(raw, h->rawp_pitch, (float*)((char*)h->rgb_half + h->rgbh_fs * f), h->rgbh_pitch, maxVal, hw2, hh2, cfa, st));
-        RUN(mfsr_stage_tracking_image(raw, h->rawp_pitch, (float*)((char*)h->gray + h->gray_fs * f), h->gray_pitch,
-                                      h->lv[0].img + h->lv[0].frame_stride * f, h->lv[0].pitch, w, hh, cfa, p.black_level, scale,
-                                      p.track_sigma, p.track_bits, st));
-        for (size_t l = 1; l < h->lv.size(); l++)
-            RUN(mfsr_stage_pyramid_down(h->lv[l - 1].img + h->lv[l - 1].frame_stride * f, h->lv[l - 1].pitch, h->lv[l - 1].w, h->lv[l - 1].h,
-                                        h->lv[l].img + h->lv[l].frame_stride * f, h->lv[l].pitch, st));
-    }
+    // one launch per burst for every per-frame kernel (grid.z = frame)
+    RUN(launch_subsample3(h->rawp, h->rawp_pitch, h->rawp_fs, h->rgb_half, h->rgbh_pitch, h->rgbh_fs, n, maxVal, hw2, hh2, cfa, st));
+    RUN(launch_tracking_image(h->rawp, h->rawp_pitch, h->rawp_fs, h->gray, h->gray_pitch, h->gray_fs, h->lv[0].img, h->lv[0].pitch, h->lv[0].frame_stride, n,
+                              w, hh, cfa, p.black_level, scale, p.track_sigma, p.track_bits, st));
+    for (size_t l = 1; l < h->lv.size(); l++)
+        RUN(launch_pyramid_down(h->lv[l - 1].img, h->lv[l - 1].pitch, h->lv[l - 1].frame_stride, h->lv[l - 1].w, h->lv[l - 1].h,
+                                h->lv[l].img, h->lv[l].pitch, h->lv[l].frame_stride, n, st));
     RUN(mfsr_stage_demosaic((const uint16_t*)((const char*)h->rawp + h->rawp_fs * h->ref_idx), h->rawp_pitch, h->rgb_ref, h->rgb_pitch,
                             w, hh, cfa, p.black_level, scale, st));
 
@@ -458,8 +458,7 @@ static int run_impl(mfsr_handle h, void* out_any, int64_t out_pitch, int out_on_
         };
         for (size_t k = 0; k < h->pal.size(); k++) {
             const Level& src = k == 0 ? h->lv.back() : h->pal[k - 1];
-            for (int f = 0; f < n; f++)
-                RUN(mfsr_stage_pyramid_down(src.img + src.frame_stride * f, src.pitch, src.w, src.h, h->pal[k].img + h->pal[k].frame_stride * f, h->pal[k].pitch, st));
+            RUN(launch_pyramid_down(src.img, src.pitch, src.frame_stride, src.w, src.h, h->pal[k].img, h->pal[k].pitch, h->pal[k].frame_stride, n, st));
         }
         const size_t ncandA = (size_t)PA_A_ANG * (2 * PA_A_R + 1) * (2 * PA_A_R + 1);
         unsigned long long* ssd = (unsigned long long*)h->pa_scratch;
@@ -529,23 +528,28 @@ static int run_impl(mfsr_handle h, void* out_any, int64_t out_pitch, int out_on_
         rb = (p.band_keep_row0 + keepn + p.band_margin + 1) & ~1; if (rb > hh) rb = hh;
     }
     const int rh = rb - ra, gy0 = p.band_row0 + ra;
-    for (int f = 0; f < n; f++)
-        RUN(launch_flow_from_tiles(h->frame_shift + (size_t)f * nt, (int64_t)tx * 8, tx, ty,
-                                   (float2*)((char*)cur + h->flow_fs * f + h->flow_pitch * ra), h->flow_pitch,
-                                   w, rh, p.base_shift[0], p.base_shift[1], p.base_rotation, gh, gy0, gty, p.band_row0 / p.tile_size, st,
-                                   pre ? h->pose + 4 * f : nullptr));
+    RUN(launch_flow_from_tiles(h->frame_shift, (int64_t)tx * 8, tx, ty, (float2*)((char*)cur + h->flow_pitch * ra), h->flow_pitch,
+                               w, rh, p.base_shift[0], p.base_shift[1], p.base_rotation, gh, gy0, gty, p.band_row0 / p.tile_size, st,
+                               pre ? h->pose : nullptr, n, (int64_t)nt * 8, h->flow_fs));
+    const float* gray_ref = (const float*)((const char*)h->gray + h->gray_fs * h->ref_idx + h->gray_pitch * ra);
     for (int it = 0; it < p.lk_iterations; it++) {
-        for (int f = 0; f < n; f++) {
-            if (f == h->ref_idx) {   // reference against itself: Iz == 0 -> UV == 0, flow unchanged
-                MFSR_CUDA_TRY(cudaMemcpyAsync((char*)nxt + h->flow_fs * f + h->flow_pitch * ra, (char*)cur + h->flow_fs * f + h->flow_pitch * ra,
-                                              (size_t)h->flow_pitch * rh, cudaMemcpyDeviceToDevice, st));
-                continue;
+        if (h->n_gray_tex == n) {
+            // texture form: one texture object per moved image, one launch per frame
+            for (int f = 0; f < n; f++) {
+                if (f == h->ref_idx) {   // reference against itself: Iz == 0 -> UV == 0, flow unchanged
+                    MFSR_CUDA_TRY(cudaMemcpyAsync((char*)nxt + h->flow_fs * f + h->flow_pitch * ra, (char*)cur + h->flow_fs * f + h->flow_pitch * ra,
+                                                  (size_t)h->flow_pitch * rh, cudaMemcpyDeviceToDevice, st));
+                    continue;
+                }
+                RUN(launch_lk_iteration(gray_ref, (const float*)((const char*)h->gray + h->gray_fs * f + h->gray_pitch * ra), h->gray_pitch,
+                                        (const float2*)((const char*)cur + h->flow_fs * f + h->flow_pitch * ra),
+                                        (float2*)((char*)nxt + h->flow_fs * f + h->flow_pitch * ra),
+                                        h->flow_pitch, w, rh, p.lk_half_window, p.lk_min_det, gh, gy0, st, h->gray_tex[f]));
             }
-            RUN(launch_lk_iteration((const float*)((const char*)h->gray + h->gray_fs * h->ref_idx + h->gray_pitch * ra),
-                                    (const float*)((const char*)h->gray + h->gray_fs * f + h->gray_pitch * ra), h->gray_pitch,
-                                    (const float2*)((const char*)cur + h->flow_fs * f + h->flow_pitch * ra),
-                                    (float2*)((char*)nxt + h->flow_fs * f + h->flow_pitch * ra),
-                                    h->flow_pitch, w, rh, p.lk_half_window, p.lk_min_det, gh, gy0, st, h->n_gray_tex == n ? h->gray_tex[f] : 0));
+        } else {
+            RUN(launch_lk_iteration(gray_ref, (const float*)((const char*)h->gray + h->gray_pitch * ra), h->gray_pitch,
+                                    (const float2*)((const char*)cur + h->flow_pitch * ra), (float2*)((char*)nxt + h->flow_pitch * ra),
+                                    h->flow_pitch, w, rh, p.lk_half_window, p.lk_min_det, gh, gy0, st, 0, n, h->gray_fs, h->flow_fs, h->ref_idx));
         }
         float2* t = cur; cur = nxt; nxt = t;
     }
@@ -557,12 +561,14 @@ static int run_impl(mfsr_handle h, void* out_any, int64_t out_pitch, int out_on_
                                  w, rh, p.tensor_box_radius, p.Dth, p.Dtr, p.kDetail, p.kDenoise, p.kStretch, p.kShrink, st));
     // ---- G. robustness masks
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_ROBUST], st));
-    for (int f = 0; f < n; f++) {
-        RUN(mfsr_stage_robustness((const float*)((const char*)h->rgb_half + h->rgbh_fs * h->ref_idx + h->rgbh_pitch * (ra / 2)),
-                                  (const float*)((const char*)h->rgb_half + h->rgbh_fs * f + h->rgbh_pitch * (ra / 2)),
-                                  h->rgbh_pitch, (const float*)((const char*)cur + h->flow_fs * f + h->flow_pitch * ra), h->flow_pitch,
-                                  (float*)((char*)h->mask + h->mask_fs * f + h->mask_pitch * (ra / 2)), h->mask_pitch, (float*)h->mask_tmp, hw2, rh / 2,
-                                  p.alpha, p.beta, p.thresholdM, p.mask_erode_radius, st));
+    // `mask_chunk` frames per launch pair: the raw certainties of a chunk stay in L2 between the two kernels
+    for (int f0 = 0; f0 < n; f0 += h->mask_chunk) {
+        const int nf = n - f0 < h->mask_chunk ? n - f0 : h->mask_chunk;
+        RUN(launch_robustness((const float*)((const char*)h->rgb_half + h->rgbh_fs * h->ref_idx + h->rgbh_pitch * (ra / 2)),
+                              (const float*)((const char*)h->rgb_half + h->rgbh_fs * f0 + h->rgbh_pitch * (ra / 2)), h->rgbh_pitch, h->rgbh_fs,
+                              (const float*)((const char*)cur + h->flow_fs * f0 + h->flow_pitch * ra), h->flow_pitch, h->flow_fs,
+                              (float*)((char*)h->mask + h->mask_fs * f0 + h->mask_pitch * (ra / 2)), h->mask_pitch, h->mask_fs,
+                              (float*)h->mask_tmp, h->mask_fs, nf, hw2, rh / 2, p.alpha, p.beta, p.thresholdM, p.mask_erode_radius, st));
         if (p.mask_erode_radius > 0) h->launches += 1;
     }
     // ---- fallback image (ApplyWeighting's inOutImg): demosaiced reference on the output grid

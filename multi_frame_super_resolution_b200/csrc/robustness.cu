@@ -6,6 +6,7 @@
 // last sample (+2,+2) survive) and parks 9 float3 per thread in dynamic shared memory; here
 // exactly the two live fetches are made and the 3x3 reference patch stays in registers.
 #include "common.cuh"
+#include "internal.h"
 
 namespace mfsr {
 
@@ -35,8 +36,11 @@ __device__ __forceinline__ Flow2 flow_fetch_half(const float2* __restrict__ flow
 __global__ void __launch_bounds__(256)
 robustness_kernel(const float* __restrict__ ref3, const float* __restrict__ mov3, int64_t rgb_pitch,
                   const float2* __restrict__ flow, int64_t flow_pitch, int fw, int fh,
-                  float4* __restrict__ mask, int64_t mask_pitch, int w, int h, float alpha, float beta, float thresholdM)
+                  float4* __restrict__ mask, int64_t mask_pitch, int w, int h, float alpha, float beta, float thresholdM, FrameStrides fs)
 {
+    mov3 = frame_ptr(mov3, fs.s[0], blockIdx.z);      // blockIdx.z = frame: moved image, its flow and its mask
+    flow = frame_ptr(flow, fs.s[1], blockIdx.z);
+    mask = frame_ptr(mask, fs.s[2], blockIdx.z);
     const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
     if (px >= w || py >= h) return;
     if (px >= w - 1 || py >= h - 1 || px < 1 || py < 1) {      // unwritten in the reference (:48): defined as 0
@@ -103,8 +107,10 @@ robustness_kernel(const float* __restrict__ ref3, const float* __restrict__ mov3
 // 2r+1 overlapping float4 loads per thread and pass).
 constexpr int ER_MAX = 8, ER_TW = 32, ER_TH = 8;
 __global__ void __launch_bounds__(256)
-erode_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t pitch, int w, int h, int r)
+erode_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t pitch, int w, int h, int r, int64_t in_fs, int64_t out_fs)
 {
+    in = frame_ptr(in, in_fs, blockIdx.z);
+    out = frame_ptr(out, out_fs, blockIdx.z);
     extern __shared__ float4 s_e[];                  // [ER_TH + 2r][ER_TW + 2r] input, then [ER_TH + 2r][ER_TW] row minima
     const int sw = ER_TW + 2 * r, sh = ER_TH + 2 * r;
     float4* s_in = s_e;
@@ -139,24 +145,34 @@ erode_kernel(const float4* __restrict__ in, float4* __restrict__ out, int64_t pi
 
 using namespace mfsr;
 
-extern "C" int mfsr_stage_robustness(const float* rgb_ref, const float* rgb_mov, int64_t rgb_pitch, const float* flow, int64_t flow_pitch,
-                                     float* mask, int64_t mask_pitch, float* scratch, int w, int h, float alpha, float beta,
-                                     float thresholdM, int erode_radius, void* stream)
+// `frames` masks per launch (frame f: rgb_mov + f * rgb_fs, flow + f * flow_fs, mask + f * mask_fs, scratch + f * scratch_fs).
+int mfsr::launch_robustness(const float* rgb_ref, const float* rgb_mov, int64_t rgb_pitch, int64_t rgb_fs, const float* flow, int64_t flow_pitch,
+                            int64_t flow_fs, float* mask, int64_t mask_pitch, int64_t mask_fs, float* scratch, int64_t scratch_fs, int frames,
+                            int w, int h, float alpha, float beta, float thresholdM, int erode_radius, cudaStream_t st)
 {
-    if (!rgb_ref || !rgb_mov || !flow || !mask || w < 3 || h < 3 || erode_radius < 0 || erode_radius > 8) return MFSR_E_INVALID;
+    if (!rgb_ref || !rgb_mov || !flow || !mask || w < 3 || h < 3 || frames < 1 || erode_radius < 0 || erode_radius > 8) return MFSR_E_INVALID;
     if (erode_radius > 0 && !scratch) return MFSR_E_INVALID;
-    cudaStream_t st = (cudaStream_t)stream;
-    dim3 b(32, 8), g(cdiv(w, 32), cdiv(h, 8));
+    dim3 b(32, 8), g(cdiv(w, 32), cdiv(h, 8), frames);
     // with a min filter the raw certainties go to `scratch` and the filter writes `mask`: every mask crosses HBM once per kernel
     float4* raw_out = erode_radius > 0 ? (float4*)scratch : (float4*)mask;
+    FrameStrides fs;
+    fs.s[0] = rgb_fs; fs.s[1] = flow_fs; fs.s[2] = erode_radius > 0 ? scratch_fs : mask_fs;
     robustness_kernel<<<g, b, 0, st>>>(rgb_ref, rgb_mov, rgb_pitch, (const float2*)flow, flow_pitch, 2 * w, 2 * h,
-                                       raw_out, mask_pitch, w, h, alpha, beta, thresholdM);
+                                       raw_out, mask_pitch, w, h, alpha, beta, thresholdM, fs);
     MFSR_LAUNCH_CHECK();
     if (erode_radius > 0) {
         const int r = erode_radius;
         const size_t smem = (size_t)((ER_TW + 2 * r) * (ER_TH + 2 * r) + ER_TW * (ER_TH + 2 * r)) * sizeof(float4);
-        erode_kernel<<<g, b, smem, st>>>((const float4*)scratch, (float4*)mask, mask_pitch, w, h, r);
+        erode_kernel<<<g, b, smem, st>>>((const float4*)scratch, (float4*)mask, mask_pitch, w, h, r, scratch_fs, mask_fs);
         MFSR_LAUNCH_CHECK();
     }
     return MFSR_OK;
+}
+
+extern "C" int mfsr_stage_robustness(const float* rgb_ref, const float* rgb_mov, int64_t rgb_pitch, const float* flow, int64_t flow_pitch,
+                                     float* mask, int64_t mask_pitch, float* scratch, int w, int h, float alpha, float beta,
+                                     float thresholdM, int erode_radius, void* stream)
+{
+    return launch_robustness(rgb_ref, rgb_mov, rgb_pitch, 0, flow, flow_pitch, 0, mask, mask_pitch, 0, scratch, 0, 1, w, h, alpha, beta, thresholdM,
+                             erode_radius, (cudaStream_t)stream);
 }

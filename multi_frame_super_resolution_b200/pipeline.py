@@ -76,6 +76,7 @@ class BurstSuperResolution:
         self._n = 0
         self._keep = None
         self._keep_ev = None
+        self._retired = []
         self._radius = None          # None: whole-burst mode
         self._seq = None             # temporal-area mode: (frames, fmt), position
         self._pos = 0
@@ -114,8 +115,10 @@ class BurstSuperResolution:
 
     def _destroy(self):
         if self._h:
-            self._lib.mfsr_destroy(self._h)
+            self._lib.mfsr_destroy(self._h)      # synchronises the handle's stream
             self._h = C.c_void_p()
+            self._retired = []
+            self._keep_ev = None
 
     def close(self):
         self._destroy()
@@ -172,9 +175,14 @@ class BurstSuperResolution:
         ptrs = (C.c_void_p * n)(*[base + i * h * w * 2 for i in range(n)])
         old = self._keep
         if isinstance(old, torch.Tensor) and old.is_cuda:
-            # device frames are read in place until the end of the run: their memory must not be handed out again by the
-            # caching allocator before the handle's stream has passed that work
-            old.record_stream(self._ext())
+            # device frames are read in place until the end of the run: their memory must not go back to the caching allocator
+            # before the handle's stream has passed that work.  (Not record_stream(): the allocator would later record an event
+            # on the handle's stream, which may be destroyed by then.)
+            self._retired = [(t, e) for (t, e) in self._retired if not e.query()]
+            if old is not frames:
+                ev = torch.cuda.Event()
+                ev.record(self._ext())
+                self._retired.append((old, ev))
         elif old is not None and self._keep_ev is not None:
             self._keep_ev.synchronize()      # host source of the async H2D copies: wait for the copies (not for the run)
         check(self._lib.mfsr_set_frames(self._h, ptrs, n, w, h, w * 2, fmt, ref_idx, on_host), "mfsr_set_frames")

@@ -70,7 +70,7 @@ def test_pipeline_vs_oracle(cuda_device, full_frame):
     assert psnr(np.where(both, out, 0), np.where(both, exp, 0)) >= 60.0            # the north star's bar
     st = sr.stage_ms()
     assert set(st) >= {"frontend", "align", "consolidate", "flow", "kernel_params", "robustness", "fallback", "merge"}
-    assert sr.launch_count() > 20
+    assert sr.launch_count() >= 15            # per-frame kernels run once per burst (grid.z = frame): about 20 launches, not ~100
     sr.close()
 
 
