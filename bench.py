@@ -278,7 +278,9 @@ def bench_dp(args, rank, world, local_rank, numa, config):
         sr.set_input(frames)
         sr.next_frame(out=out_dev)
     sampler = ClockSampler(local_rank); sampler.start()
+    torch.cuda.cudart().cudaProfilerStart()     # `ncu --profile-from-start off` lists exactly the timed steps (profiles/*_launches.txt); a no-op otherwise
     ms_total, launches = time_resident(frames, args.steps)
+    torch.cuda.cudart().cudaProfilerStop()
     stage_last = sr.stage_ms()
     merge_ms = []
     for _ in range(args.steps):                 # merge kernel: average launch duration, each launch preceded by the rest of the chain
