@@ -99,7 +99,7 @@ typedef struct mfsr_params {
     int   pair_span;          /* measured pairs (i,j), 0 < j-i <= pair_span                  */
     int   track_bits;         /* tracking image quantisation (7 -> exact fp32 SSD, T=16)     */
     float track_sigma;        /* gaussin_filter_1D sigma (main.cpp:370,1868) = 0.5           */
-    float min_threshold;      /* findMinimum `threshold` (kernel.cu:519)                     */
+    float min_threshold;      /* findMinimum `threshold` (kernel.cu:519): SSD span below which a tile gets a zero shift; default 1024 */
     float base_shift[2];      /* global pre-alignment (kernel.cu:275-276); 0 = disabled      */
     float base_rotation;
     /* optical flow */

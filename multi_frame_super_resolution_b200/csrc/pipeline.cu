@@ -131,7 +131,7 @@ extern "C" int mfsr_default_params(mfsr_params* p)
     p->cfa[0] = MFSR_RED; p->cfa[1] = MFSR_GREEN; p->cfa[2] = MFSR_GREEN; p->cfa[3] = MFSR_BLUE;
     for (int c = 0; c < 3; c++) { p->black_level[c] = 64.0f; p->white_level[c] = 1023.0f - 64.0f; }
     p->tile_size = 16; p->max_shift = 4; p->levels = 4; p->pair_span = 2; p->track_bits = 7; p->track_sigma = 0.5f;
-    p->min_threshold = 0.0f;
+    p->min_threshold = 1024.0f;     // flat SSD surface (max - min below ~2 grey levels rms over a 16x16 tile): zero shift instead of a noise arg-min (tools/threshold_sweep.py)
     p->lk_iterations = 3; p->lk_half_window = 3; p->lk_min_det = 1e-3f;
     p->Dth = 0.005f; p->Dtr = 0.012f; p->kDetail = 0.3f; p->kDenoise = 4.0f; p->kStretch = 4.0f; p->kShrink = 2.0f;
     p->tensor_box_radius = 2;

@@ -361,7 +361,7 @@ def default_params(**kw):
     of bench.py runs from here without loading the product package."""
     from types import SimpleNamespace
     d = dict(scale=2, full_frame=1, cfa=[0, 1, 1, 2], black_level=[64.0] * 3, white_level=[959.0] * 3, tile_size=16, max_shift=4,
-             levels=4, pair_span=2, track_bits=7, track_sigma=0.5, min_threshold=0.0, base_shift=[0.0, 0.0], base_rotation=0.0,
+             levels=4, pair_span=2, track_bits=7, track_sigma=0.5, min_threshold=1024.0, base_shift=[0.0, 0.0], base_rotation=0.0,
              lk_iterations=3, lk_half_window=3, lk_min_det=1e-3, Dth=0.005, Dtr=0.012, kDetail=0.3, kDenoise=4.0, kStretch=4.0,
              kShrink=2.0, tensor_box_radius=2, alpha=1e-3, beta=1e-5, thresholdM=0.8, mask_erode_radius=2,
              weight_threshold=0.1, merge_flags=0, prealign=0, lk_texture=0)
