@@ -45,14 +45,30 @@ def test_merge_reference_geometry_vs_oracle(cuda_device, n, h, w):
     assert np.array_equal(out[0], fb.numpy()[0]) and np.array_equal(out[:, -1], fb.numpy()[:, -1])
 
 
-@pytest.mark.parametrize("scale", [1, 2, 3])
+@pytest.mark.parametrize("scale", [1, 2, 3, 4])
 def test_merge_full_frame_scales_vs_oracle(cuda_device, scale):
+    """Scale 1: accumulateImages; 2: the slot kernel; 3, 4: the lean tap loop (merge_lean_kernel); all against the oracle's tap loop."""
     n, h, w = 4, 64, 96
     raw, mask, flow, kern, g = _inputs(n, h, w, 31 + scale, cuda_device)
     geom = MergeGeom.full_frame(w, h, scale)
     fb = torch.rand((geom.out_h, geom.out_w, 3), generator=g)
     out, s, wt, exp, es, ew = _run_both(raw, mask, flow, kern, fb, geom, cuda_device, gamma=(scale == 2))
     assert max_abs(out, exp) <= TOL_MAXABS and psnr(out, exp) >= TOL_PSNR
+
+
+def test_merge_lean_kernel_large_shifts_and_bad_certainties(cuda_device):
+    """Scale 3 (merge_lean_kernel) with large shifts (taps run into the clamp range) and non-finite certainties, against the oracle's
+    tap loop, accumulators included."""
+    n, h, w = 6, 96, 128
+    raw, mask, flow, kern, g = _inputs(n, h, w, 77, cuda_device)
+    flow = flow * 6.0                                      # shifts of up to ~ +-18 HR px at 3x: taps run into the clamp range
+    mask[1, 5:9, 7:11, 0] = float("nan")
+    mask[2, 20:22, 30:40, 1] = float("inf")
+    geom = MergeGeom.full_frame(w, h, 3)
+    fb = torch.rand((geom.out_h, geom.out_w, 3), generator=g)
+    out, s, wt, exp, es, ew = _run_both(raw, mask, flow, kern, fb, geom, cuda_device)
+    assert max_abs(out, exp) <= TOL_MAXABS and psnr(out, exp) >= TOL_PSNR
+    assert np.allclose(s, es, rtol=5e-5, atol=5e-5) and np.allclose(wt, ew, rtol=5e-5, atol=5e-5)
 
 
 def test_merge_edge_cases(cuda_device):
