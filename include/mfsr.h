@@ -263,7 +263,8 @@ int mfsr_stage_kernel_params(const float* gray, int64_t gray_pitch,
  * RobustnessModell.cu:67-70) followed by a (2r+1)^2 min filter on .xyz.
  *   flow: full-resolution float2 flow (2*w x 2*h), sampled like the texture.
  *   mask: float4 w x h; border pixels are 0 (unwritten in the reference).
- *   scratch: float4 w x h work buffer (required when erode_radius > 0).     */
+ *   scratch: float4 w x h work buffer for the two-kernel form (certainty, then min filter); NULL with erode_radius > 0
+ *   selects the fused kernel (what mfsr_run uses): same mask, bit for bit, no intermediate image.     */
 int mfsr_stage_robustness(const float* rgb_ref, const float* rgb_mov, int64_t rgb_pitch,
                           const float* flow, int64_t flow_pitch,
                           float* mask, int64_t mask_pitch, float* scratch,

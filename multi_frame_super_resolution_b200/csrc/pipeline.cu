@@ -51,7 +51,7 @@ struct mfsr_context {
     float* gray; int64_t gray_pitch, gray_fs;
     float* rgb_ref; int64_t rgb_pitch;
     float2* flowA; float2* flowB; int64_t flow_pitch, flow_fs;
-    float4* mask; float4* mask_tmp; int64_t mask_pitch, mask_fs, mask_tmp_cap; int mask_chunk;
+    float4* mask; int64_t mask_pitch, mask_fs;
     float4* kern; int64_t kern_pitch;
     float* fallback; float* outbuf; int64_t out_pitch_own;
     float* part_sum; float* part_weight;               // partial sums of the frame-chunked merge (bursts of more than 10 frames), else null
@@ -238,10 +238,6 @@ static size_t carve(mfsr_context* c, char* base, int n, int w, int h)
     c->flowB = (float2*)take((size_t)c->flow_fs * n);
     c->mask_pitch = (int64_t)hw * 16; c->mask_fs = c->mask_pitch * hh;
     c->mask = (float4*)take((size_t)c->mask_fs * n);
-    // scratch of the min filter: as many frames as fit in about half of the L2 (at least one)
-    if (!base) c->mask_tmp_cap = c->mask_fs * std::min<int64_t>(n, std::max<int64_t>(1, (48ll << 20) / c->mask_fs));      // sized at create
-    c->mask_chunk = (int)std::min<int64_t>(n, std::max<int64_t>(1, c->mask_tmp_cap / c->mask_fs));
-    c->mask_tmp = (float4*)take((size_t)c->mask_fs * c->mask_chunk);
     c->kern_pitch = (int64_t)w * 16;
     c->kern = (float4*)take((size_t)c->kern_pitch * h);
     mfsr_merge_geom g; make_geom(p, w, h, &g);
@@ -590,16 +586,12 @@ static int run_impl(mfsr_handle h, void* out_any, int64_t out_pitch, int out_on_
                                  w, rh, p.tensor_box_radius, p.Dth, p.Dtr, p.kDetail, p.kDenoise, p.kStretch, p.kShrink, st));
     // ---- G. robustness masks
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_ROBUST], st));
-    // `mask_chunk` frames per launch pair: the raw certainties of a chunk stay in L2 between the two kernels
-    for (int f0 = 0; f0 < n; f0 += h->mask_chunk) {
-        const int nf = n - f0 < h->mask_chunk ? n - f0 : h->mask_chunk;
-        RUN(launch_robustness((const float*)((const char*)h->rgb_half + h->rgbh_fs * h->ref_idx + h->rgbh_pitch * (ra / 2)),
-                              (const float*)((const char*)h->rgb_half + h->rgbh_fs * f0 + h->rgbh_pitch * (ra / 2)), h->rgbh_pitch, h->rgbh_fs,
-                              (const float*)((const char*)cur + h->flow_fs * f0 + h->flow_pitch * ra), h->flow_pitch, h->flow_fs,
-                              (float*)((char*)h->mask + h->mask_fs * f0 + h->mask_pitch * (ra / 2)), h->mask_pitch, h->mask_fs,
-                              (float*)h->mask_tmp, h->mask_fs, nf, hw2, rh / 2, p.alpha, p.beta, p.thresholdM, p.mask_erode_radius, st));
-        if (p.mask_erode_radius > 0) h->launches += 1;
-    }
+    // all frames in one launch; with a min filter the fused kernel (certainty + row / column minima in shared memory)
+    RUN(launch_robustness((const float*)((const char*)h->rgb_half + h->rgbh_fs * h->ref_idx + h->rgbh_pitch * (ra / 2)),
+                          (const float*)((const char*)h->rgb_half + h->rgbh_pitch * (ra / 2)), h->rgbh_pitch, h->rgbh_fs,
+                          (const float*)((const char*)cur + h->flow_pitch * ra), h->flow_pitch, h->flow_fs,
+                          (float*)((char*)h->mask + h->mask_pitch * (ra / 2)), h->mask_pitch, h->mask_fs,
+                          nullptr, 0, n, hw2, rh / 2, p.alpha, p.beta, p.thresholdM, p.mask_erode_radius, st));
     // ---- fallback image (ApplyWeighting's inOutImg): demosaiced reference on the output grid
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_FALLBACK], st));
     // Row-band mode: the reference leaves the 1-pixel border of the merge WINDOW untouched (DeBayerKernels.cu:391).  At an

@@ -33,20 +33,12 @@ __device__ __forceinline__ Flow2 flow_fetch_half(const float2* __restrict__ flow
     return r;
 }
 
-__global__ void __launch_bounds__(256)
-robustness_kernel(const float* __restrict__ ref3, const float* __restrict__ mov3, int64_t rgb_pitch,
-                  const float2* __restrict__ flow, int64_t flow_pitch, int fw, int fh,
-                  float4* __restrict__ mask, int64_t mask_pitch, int w, int h, float alpha, float beta, float thresholdM, FrameStrides fs)
+// Certainty of half-resolution pixel (px, py); 0 on the 1-pixel border the reference leaves unwritten (:48).
+__device__ __forceinline__ float4 robust_px(const float* __restrict__ ref3, const float* __restrict__ mov3, int64_t rgb_pitch,
+                                            const float2* __restrict__ flow, int64_t flow_pitch, int fw, int fh,
+                                            int w, int h, int px, int py, float alpha, float beta, float thresholdM)
 {
-    mov3 = frame_ptr(mov3, fs.s[0], blockIdx.z);      // blockIdx.z = frame: moved image, its flow and its mask
-    flow = frame_ptr(flow, fs.s[1], blockIdx.z);
-    mask = frame_ptr(mask, fs.s[2], blockIdx.z);
-    const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
-    if (px >= w || py >= h) return;
-    if (px >= w - 1 || py >= h - 1 || px < 1 || py < 1) {      // unwritten in the reference (:48): defined as 0
-        row_ptr(mask, mask_pitch, py)[px] = make_float4(0.f, 0.f, 0.f, 0.f);
-        return;
-    }
+    if (px >= w - 1 || py >= h - 1 || px < 1 || py < 1) return make_float4(0.f, 0.f, 0.f, 0.f);
     const Flow2 sf = flow_fetch_half(flow, flow_pitch, fw, fh, px, py);
     const Flow2 sl = flow_fetch_half(flow, flow_pitch, fw, fh, px + 2, py + 2);
     float maxx = fmaxf(sl.x, sf.x), maxy = fmaxf(sl.y, sf.y), minx = fminf(sl.x, sf.x), miny = fminf(sl.y, sf.y);
@@ -99,7 +91,67 @@ robustness_kernel(const float* __restrict__ ref3, const float* __restrict__ mov3
         dist = dist * (sd * sd * rb_rcp(sd * sd + sigmaMD * sigmaMD));
         mk[c] = fmaxf(fminf(s * __expf(-dist * dist * rb_rcp(sigma * sigma)) - tt, 1.0f), 0.0f);
     }
-    row_ptr(mask, mask_pitch, py)[px] = make_float4(mk[0], mk[1], mk[2], Mv);
+    return make_float4(mk[0], mk[1], mk[2], Mv);
+}
+
+__global__ void __launch_bounds__(256)
+robustness_kernel(const float* __restrict__ ref3, const float* __restrict__ mov3, int64_t rgb_pitch,
+                  const float2* __restrict__ flow, int64_t flow_pitch, int fw, int fh,
+                  float4* __restrict__ mask, int64_t mask_pitch, int w, int h, float alpha, float beta, float thresholdM, FrameStrides fs)
+{
+    mov3 = frame_ptr(mov3, fs.s[0], blockIdx.z);      // blockIdx.z = frame: moved image, its flow and its mask
+    flow = frame_ptr(flow, fs.s[1], blockIdx.z);
+    mask = frame_ptr(mask, fs.s[2], blockIdx.z);
+    const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+    if (px >= w || py >= h) return;
+    row_ptr(mask, mask_pitch, py)[px] = robust_px(ref3, mov3, rgb_pitch, flow, flow_pitch, fw, fh, w, h, px, py, alpha, beta, thresholdM);
+}
+
+// Robustness + (2r+1)^2 min filter in ONE launch (round 2): the certainties of a 48 x 32 region (output tile (48 - 2r) x (32 - 2r) plus its
+// halo, clamp border) are computed straight into shared memory, row minima, then column minima — the raw certainties never go to HBM
+// (the two-kernel form wrote and re-read a 48 MB float4 mask per 12 MP frame) for 1.25 x the certainty arithmetic at r = 2.
+// Same per-pixel function and the same min order as robustness_kernel + erode_kernel: bit-identical masks.
+constexpr int RE_W = 48, RE_H = 32;
+__global__ void __launch_bounds__(256)
+robust_erode_kernel(const float* __restrict__ ref3, const float* __restrict__ mov3, int64_t rgb_pitch,
+                    const float2* __restrict__ flow, int64_t flow_pitch, int fw, int fh,
+                    float4* __restrict__ mask, int64_t mask_pitch, int w, int h, float alpha, float beta, float thresholdM, int r, FrameStrides fs)
+{
+    extern __shared__ float4 s_re[];                 // [RE_H][RE_W] certainties, then [RE_H][RE_W - 2r] row minima
+    mov3 = frame_ptr(mov3, fs.s[0], blockIdx.z);
+    flow = frame_ptr(flow, fs.s[1], blockIdx.z);
+    mask = frame_ptr(mask, fs.s[2], blockIdx.z);
+    const int iw = RE_W - 2 * r, ih = RE_H - 2 * r;
+    float4* s_in = s_re;
+    float4* s_row = s_re + RE_W * RE_H;
+    const int x0 = blockIdx.x * iw, y0 = blockIdx.y * ih, tid = threadIdx.y * blockDim.x + threadIdx.x;
+    for (int i = tid; i < RE_W * RE_H; i += 256) {
+        const int ly = i / RE_W, lx = i - ly * RE_W;
+        s_in[i] = robust_px(ref3, mov3, rgb_pitch, flow, flow_pitch, fw, fh, w, h, clampi(x0 + lx - r, 0, w - 1), clampi(y0 + ly - r, 0, h - 1),
+                            alpha, beta, thresholdM);
+    }
+    __syncthreads();
+    for (int i = tid; i < iw * RE_H; i += 256) {
+        const int ly = i / iw, lx = i - ly * iw;
+        float4 m = s_in[ly * RE_W + lx + r];
+        for (int d = 0; d <= 2 * r; d++) {
+            const float4 v = s_in[ly * RE_W + lx + d];
+            m.x = fminf(m.x, v.x); m.y = fminf(m.y, v.y); m.z = fminf(m.z, v.z);
+        }
+        s_row[i] = m;
+    }
+    __syncthreads();
+    for (int i = tid; i < iw * ih; i += 256) {
+        const int ly = i / iw, lx = i - ly * iw;
+        const int x = x0 + lx, y = y0 + ly;
+        if (x >= w || y >= h) continue;
+        float4 m = s_row[(ly + r) * iw + lx];
+        for (int d = 0; d <= 2 * r; d++) {
+            const float4 v = s_row[(ly + d) * iw + lx];
+            m.x = fminf(m.x, v.x); m.y = fminf(m.y, v.y); m.z = fminf(m.z, v.z);
+        }
+        row_ptr(mask, mask_pitch, y)[x] = m;
+    }
 }
 
 // (2r+1)^2 min filter on .xyz, clamp border; .w copied.  One launch: a 32 x 8 output tile with its halo is staged in shared
@@ -151,8 +203,19 @@ int mfsr::launch_robustness(const float* rgb_ref, const float* rgb_mov, int64_t 
                             int w, int h, float alpha, float beta, float thresholdM, int erode_radius, cudaStream_t st)
 {
     if (!rgb_ref || !rgb_mov || !flow || !mask || w < 3 || h < 3 || frames < 1 || erode_radius < 0 || erode_radius > 8) return MFSR_E_INVALID;
-    if (erode_radius > 0 && !scratch) return MFSR_E_INVALID;
     dim3 b(32, 8), g(cdiv(w, 32), cdiv(h, 8), frames);
+    if (erode_radius > 0 && !scratch) {
+        // fused form (what mfsr_run uses): no scratch image
+        const int r = erode_radius;
+        FrameStrides ff;
+        ff.s[0] = rgb_fs; ff.s[1] = flow_fs; ff.s[2] = mask_fs;
+        const size_t smem = (size_t)(RE_W * RE_H + (RE_W - 2 * r) * RE_H) * sizeof(float4);
+        dim3 gf(cdiv(w, RE_W - 2 * r), cdiv(h, RE_H - 2 * r), frames);
+        robust_erode_kernel<<<gf, b, smem, st>>>(rgb_ref, rgb_mov, rgb_pitch, (const float2*)flow, flow_pitch, 2 * w, 2 * h,
+                                                 (float4*)mask, mask_pitch, w, h, alpha, beta, thresholdM, r, ff);
+        MFSR_LAUNCH_CHECK();
+        return MFSR_OK;
+    }
     // with a min filter the raw certainties go to `scratch` and the filter writes `mask`: every mask crosses HBM once per kernel
     float4* raw_out = erode_radius > 0 ? (float4*)scratch : (float4*)mask;
     FrameStrides fs;

@@ -168,12 +168,13 @@ def kernel_params(gray, box_radius=2, Dth=0.005, Dtr=0.012, kDetail=0.3, kDenois
     return out
 
 
-def robustness(rgb_ref, rgb_mov, flow, alpha, beta, threshold_m, erode_radius=0):
-    """rgb_*: [h, w, 3] half-res; flow: [2h, 2w, 2]."""
+def robustness(rgb_ref, rgb_mov, flow, alpha, beta, threshold_m, erode_radius=0, fused=True):
+    """rgb_*: [h, w, 3] half-res; flow: [2h, 2w, 2].  fused=False: certainty kernel + min-filter kernel through a scratch image;
+    fused=True (what mfsr_run does): one kernel, same mask."""
     _cuda(rgb_ref, rgb_mov, flow)
     h, w = rgb_ref.shape[:2]
     mask = torch.empty((h, w, 4), dtype=torch.float32, device=rgb_ref.device)
-    scratch = torch.empty_like(mask) if erode_radius > 0 else None
+    scratch = torch.empty_like(mask) if (erode_radius > 0 and not fused) else None
     check(_lib.load().mfsr_stage_robustness(_p(rgb_ref), _p(rgb_mov), w * 12, _p(flow), flow.shape[1] * 8, _p(mask), w * 16,
                                             _p(scratch), w, h, float(alpha), float(beta), float(threshold_m), erode_radius, _stream()),
           "mfsr_stage_robustness")

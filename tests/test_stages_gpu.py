@@ -364,6 +364,21 @@ def test_robustness_vs_oracle(cuda_device, burst):
 
 
 @needs_ref
+
+def test_robustness_fused_equals_two_kernels(cuda_device, burst):
+    """Certainty + min filter in one launch (robust_erode_kernel) against the two-kernel form, every radius, odd sizes: bit-identical."""
+    fr, _ = burst
+    rgb = [stages.subsample3(fr[i].to(cuda_device), 1023.0) for i in range(2)]
+    h, w = rgb[0].shape[:2]
+    g = torch.Generator().manual_seed(5)
+    flow = ((torch.rand((2 * h, 2 * w, 2), generator=g) - 0.5) * 6).to(cuda_device)
+    for (hh, ww) in ((h, w), (h - 3, w - 5)):
+        a, b, f = rgb[0][:hh, :ww].contiguous(), rgb[1][:hh, :ww].contiguous(), flow[:2 * hh, :2 * ww].contiguous()
+        for er in (1, 2, 3, 8):
+            two = stages.robustness(a, b, f, 1e-3, 1e-5, 0.8, er, fused=False)
+            one = stages.robustness(a, b, f, 1e-3, 1e-5, 0.8, er, fused=True)
+            assert torch.equal(one, two), (hh, ww, er)
+
 @pytest.mark.parametrize("varying", [False, True])
 def test_robustness_vs_reference_kernel(cuda_device, burst, varying):
     """Constant flow and a smoothly varying one (the texture fetch of RobustnessModell.cu:58 lands on the .5 / .5 position of the
