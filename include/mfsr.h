@@ -274,9 +274,17 @@ int mfsr_stage_robustness(const float* rgb_ref, const float* rgb_mov, int64_t rg
 /* Geometry of a merge launch.  Reference geometry for raw dims (dimX,dimY):
  *   scale=2, out_w=dimX, out_h=dimY, org_x=dimX/2, org_y=dimY/2,
  *   clamp = [dimX/4, dimX/4+dimX/2-1] x [dimY/4, dimY/4+dimY/2-1].        */
+/* Scale factors: a plain integer s (1, 2, 3, 4 ...; the reference hard-codes 2, DeBayerKernels.cu:414-423), or a rational
+ * num / den encoded in the same int (den in the upper half, 0 == 1): MFSR_SCALE_RATIONAL(3, 2) is 1.5x.  With a rational scale
+ * every "/ s" of the reference becomes "* den / num" (integer taps: ((X + px + sx) * den) / num, texture coordinate
+ * ((X + 0.5) * den) / num, integer shift round(flow * num / den)); integer scales are the den == 1 case, bit for bit. */
+#define MFSR_SCALE_RATIONAL(num, den) ((int)(((unsigned)(den) << 16) | (unsigned)(num)))
+#define MFSR_SCALE_NUM(s) ((int)((unsigned)(s) & 0xffffu))
+#define MFSR_SCALE_DEN(s) ((int)((((unsigned)(s) >> 16) & 0xffffu) ? (((unsigned)(s) >> 16) & 0xffffu) : 1u))
+
 typedef struct mfsr_merge_geom {
     int raw_w, raw_h;        /* dimX, dimY of the raw frames                           */
-    int scale;               /* s                                                       */
+    int scale;               /* s, or MFSR_SCALE_RATIONAL(num, den)                    */
     int out_w, out_h;        /* output window size in HR pixels                        */
     int org_x, org_y;        /* HR coordinate of output pixel (0,0)                    */
     int clamp_x0, clamp_x1;  /* inclusive raw-coordinate clamp of the taps             */

@@ -42,6 +42,11 @@ class Params(C.Structure):
     ]
 
 
+def scale_rational(num: int, den: int) -> int:
+    """include/mfsr.h MFSR_SCALE_RATIONAL: num / den as a scale value (scale_rational(3, 2) = 1.5x)."""
+    return (den << 16) | num
+
+
 class MergeGeom(C.Structure):
     """Mirror of `mfsr_merge_geom`."""
     _fields_ = [("raw_w", c_i), ("raw_h", c_i), ("scale", c_i), ("out_w", c_i), ("out_h", c_i),
@@ -56,7 +61,8 @@ class MergeGeom(C.Structure):
 
     @classmethod
     def full_frame(cls, raw_w: int, raw_h: int, scale: int) -> "MergeGeom":
-        return cls(raw_w, raw_h, scale, raw_w * scale, raw_h * scale, 0, 0, 0, raw_w - 1, 0, raw_h - 1)
+        num, den = scale & 0xffff, ((scale >> 16) & 0xffff) or 1      # scale_rational(num, den)
+        return cls(raw_w, raw_h, scale, raw_w * num // den, raw_h * num // den, 0, 0, 0, raw_w - 1, 0, raw_h - 1)
 
     @classmethod
     def one_to_one(cls, raw_w: int, raw_h: int) -> "MergeGeom":

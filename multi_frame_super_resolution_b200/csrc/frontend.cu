@@ -426,14 +426,14 @@ fallback_upsample_kernel(const float* __restrict__ rgb, int64_t rgb_pitch, int w
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, yb = (blockIdx.y * blockDim.y + threadIdx.y) * FBU_ROWS;
     if (x >= g.out_w || yb >= g.out_h) return;
-    const float fs = (float)g.scale;
-    const TexAxis tx = tex_axis(__fdiv_rn((float)(x + g.org_x) + 0.5f, fs), w);
+    const float fs = (float)MFSR_SCALE_NUM(g.scale), fd = (float)MFSR_SCALE_DEN(g.scale);      // ((X + 0.5) * den) / num; den == 1: exact factor
+    const TexAxis tx = tex_axis(__fdiv_rn(__fmul_rn((float)(x + g.org_x) + 0.5f, fd), fs), w);
     const int o0 = 3 * tx.i0, o1 = 3 * tx.i1;
 #pragma unroll 2
     for (int r = 0; r < FBU_ROWS; r++) {
         const int y = yb + r;
         if (y >= g.out_h) break;
-        const TexAxis ty = tex_axis(__fdiv_rn((float)(y + g.org_y) + 0.5f, fs), h);
+        const TexAxis ty = tex_axis(__fdiv_rn(__fmul_rn((float)(y + g.org_y) + 0.5f, fd), fs), h);
         const float* r0 = row_ptr(rgb, rgb_pitch, ty.i0);
         const float* r1 = row_ptr(rgb, rgb_pitch, ty.i1);
         float* o = row_ptr(out, out_pitch, y) + 3 * x;

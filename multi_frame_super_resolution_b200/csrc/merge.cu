@@ -27,12 +27,15 @@ merge_generic_kernel(const __grid_constant__ MergeArgs A)
     if (x >= g.out_w || y >= g.out_h) return;
 
     float acc[3] = {0.f, 0.f, 0.f}, wacc[3] = {0.f, 0.f, 0.f};
-    const int s = S ? S : g.scale;
+    // S == 0: the scale comes from the geometry and may be rational (MFSR_SCALE_RATIONAL(num, den)): "/ s" is "* den / num"
+    const int s = S ? S : MFSR_SCALE_NUM(g.scale), den = S ? 1 : MFSR_SCALE_DEN(g.scale);
+    const float sf = S ? (float)S : __fdiv_rn((float)s, (float)den);
     // the reference skips the 1-px border of the output window (DeBayerKernels.cu:391)
     const bool interior = !(x < 1 || y < 1 || x >= g.out_w - 1 || y >= g.out_h - 1);
     if (interior) {
         const int X = x + g.org_x, Y = y + g.org_y;
-        const float u = __fdiv_rn((float)X + 0.5f, (float)s), v = __fdiv_rn((float)Y + 0.5f, (float)s);
+        const float u = S ? __fdiv_rn((float)X + 0.5f, (float)s) : __fdiv_rn(__fmul_rn((float)X + 0.5f, (float)den), (float)s);
+        const float v = S ? __fdiv_rn((float)Y + 0.5f, (float)s) : __fdiv_rn(__fmul_rn((float)Y + 0.5f, (float)den), (float)s);
         const TexAxis tx = tex_axis(u, g.raw_w), ty = tex_axis(v, g.raw_h);
         // kernel parameter fetch (float4 texture, :401)
         float kx, ky, kz;
@@ -60,18 +63,18 @@ merge_generic_kernel(const __grid_constant__ MergeArgs A)
             const float4* mask = (const float4*)((const char*)A.mask + A.mask_fs * f);
             const float2 s00 = row_ptr(flow, A.flow_pitch, ty.i0)[tx.i0], s10 = row_ptr(flow, A.flow_pitch, ty.i0)[tx.i1];
             const float2 s01 = row_ptr(flow, A.flow_pitch, ty.i1)[tx.i0], s11 = row_ptr(flow, A.flow_pitch, ty.i1)[tx.i1];
-            const int sx = (int)roundf(__fmul_rn(tex_mix(s00.x, s10.x, s01.x, s11.x, tx.a, ty.a), (float)s));
-            const int sy = (int)roundf(__fmul_rn(tex_mix(s00.y, s10.y, s01.y, s11.y, tx.a, ty.a), (float)s));
+            const int sx = (int)roundf(__fmul_rn(tex_mix(s00.x, s10.x, s01.x, s11.x, tx.a, ty.a), sf));
+            const int sy = (int)roundf(__fmul_rn(tex_mix(s00.y, s10.y, s01.y, s11.y, tx.a, ty.a), sf));
 #pragma unroll
             for (int py = -2; py <= 2; py++) {
-                const int ppsy = min(max((Y + py + sy) / s, g.clamp_y0), g.clamp_y1);
-                const int ppy = min(max((Y + py) / s, g.clamp_y0), g.clamp_y1);
+                const int ppsy = min(max((Y + py + sy) * den / s, g.clamp_y0), g.clamp_y1);
+                const int ppy = min(max((Y + py) * den / s, g.clamp_y0), g.clamp_y1);
                 const uint16_t* rrow = row_ptr(raw, A.raw_pitch, ppsy);
                 const float4* mrow = row_ptr(mask, A.mask_pitch, ppy / 2);
 #pragma unroll
                 for (int px = -2; px <= 2; px++) {
-                    const int ppsx = min(max((X + px + sx) / s, g.clamp_x0), g.clamp_x1);
-                    const int ppx = min(max((X + px) / s, g.clamp_x0), g.clamp_x1);
+                    const int ppsx = min(max((X + px + sx) * den / s, g.clamp_x0), g.clamp_x1);
+                    const int ppx = min(max((X + px) * den / s, g.clamp_x0), g.clamp_x1);
                     const int col = A.cfa.c[(ppsy & 1) * 2 + (ppsx & 1)];
                     const float wt = w[(py + 2) * 5 + (px + 2)];
                     const float r = (float)__ldg(rrow + ppsx);
@@ -276,7 +279,7 @@ extern "C" int mfsr_stage_merge(const uint16_t* raw, int64_t raw_pitch, int64_t 
 {
     if (!kernel4 || !out || !geom || !cfa || !white || !black) return MFSR_E_INVALID;
     if (n_frames > 0 && (!raw || !mask || !flow)) return MFSR_E_INVALID;
-    if (n_frames < 0 || geom->scale < 1 || geom->out_w <= 0 || geom->out_h <= 0) return MFSR_E_INVALID;
+    if (n_frames < 0 || geom->scale < 1 || MFSR_SCALE_NUM(geom->scale) < 1 || geom->out_w <= 0 || geom->out_h <= 0) return MFSR_E_INVALID;
     if (!fallback && !(flags & MFSR_MERGE_NO_FALLBACK)) return MFSR_E_INVALID;
     if ((sum_out == nullptr) != (weight_out == nullptr)) return MFSR_E_INVALID;
     if (geom->clamp_x0 < 0 || geom->clamp_x1 >= geom->raw_w || geom->clamp_y0 < 0 || geom->clamp_y1 >= geom->raw_h ||

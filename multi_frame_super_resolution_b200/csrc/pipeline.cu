@@ -125,7 +125,8 @@ static void make_geom(const mfsr_params& p, int w, int h, mfsr_merge_geom* g)
         g->out_w = w * p.scale; g->out_h = keepn * p.scale; g->org_x = 0; g->org_y = keep0 * p.scale;
         g->clamp_x0 = 0; g->clamp_x1 = w - 1; g->clamp_y0 = 0; g->clamp_y1 = h - 1;
     } else if (p.full_frame) {
-        g->out_w = w * p.scale; g->out_h = h * p.scale; g->org_x = 0; g->org_y = 0;
+        const int num = MFSR_SCALE_NUM(p.scale), den = MFSR_SCALE_DEN(p.scale);
+        g->out_w = w * num / den; g->out_h = h * num / den; g->org_x = 0; g->org_y = 0;
         g->clamp_x0 = 0; g->clamp_x1 = w - 1; g->clamp_y0 = 0; g->clamp_y1 = h - 1;
     } else {
         // generalisation of DeBayerKernels.cu:398-423 (s = 2: org = dim/2, clamp = [dim/4, dim/4 + dim/2 - 1])
@@ -184,7 +185,12 @@ extern "C" int mfsr_device_count(void)
 static int validate_params(const mfsr_params* p)
 {
     if (!p || p->abi_version != MFSR_ABI_VERSION) return MFSR_E_INVALID;
-    if (p->scale < 1 || p->scale > 4) return MFSR_E_INVALID;
+    {
+        // integer scales 1..4, or a rational MFSR_SCALE_RATIONAL(num, den) with 1 <= num / den <= 4 on the full frame (not in a row band)
+        const int num = MFSR_SCALE_NUM(p->scale), den = MFSR_SCALE_DEN(p->scale);
+        if (p->scale < 1 || num < den || num > 4 * den || den > 16) return MFSR_E_INVALID;
+        if (den > 1 && (!p->full_frame || p->band_global_h > 0)) return MFSR_E_INVALID;
+    }
     if (p->tile_size < 4 || (p->tile_size & 3) || p->max_shift < 1 || p->levels < 1 || p->levels > 8) return MFSR_E_INVALID;
     if (p->pair_span < 1 || p->track_bits < 1 || p->track_bits > 8) return MFSR_E_INVALID;
     // exactness contract of the integer SSD (align.cu): 2 * T^2 * qmax^2 < 2^24

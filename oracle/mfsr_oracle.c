@@ -877,27 +877,30 @@ void orc_mask_erode(const float* in4, float* out4, int w, int h, int r)
 void orc_accumulate(const uint16_t* raw, float* sum3, float* weight3, const float* mask4, const float* kernel4,
                     const float* flow2, const orc_merge_geom* g, const int cfa[4], const float white[3], const float black[3])
 {
-    int dimX = g->raw_w, dimY = g->raw_h, s = g->scale, mw = dimX / 2;
+    /* rational scale num / den (include/mfsr.h MFSR_SCALE_RATIONAL; den == 1: the reference's integer arithmetic, the factor 1
+     * changes nothing): "/ s" becomes "* den / num" */
+    int dimX = g->raw_w, dimY = g->raw_h, s = g->scale & 0xffff, den = ((g->scale >> 16) & 0xffff) ? ((g->scale >> 16) & 0xffff) : 1, mw = dimX / 2;
+    const float sf = (float)s / (float)den;
 #pragma omp parallel for schedule(static)
     for (int y = 1; y < g->out_h - 1; y++)
         for (int x = 1; x < g->out_w - 1; x++) {
             float* pixel = sum3 + 3 * ((size_t)y * g->out_w + x);
             float* tw = weight3 + 3 * ((size_t)y * g->out_w + x);
             int X = x + g->org_x, Y = y + g->org_y;
-            float u = ((float)X + 0.5f) / (float)s, v = ((float)Y + 0.5f) / (float)s;
+            float u = (((float)X + 0.5f) * (float)den) / (float)s, v = (((float)Y + 0.5f) * (float)den) / (float)s;
             float kx = tex_lin(kernel4, dimX, dimY, 4, 0, u, v);
             float ky = tex_lin(kernel4, dimX, dimY, 4, 1, u, v);
             float kz = tex_lin(kernel4, dimX, dimY, 4, 2, u, v);
-            float shx = roundf(tex_lin(flow2, dimX, dimY, 2, 0, u, v) * (float)s);
-            float shy = roundf(tex_lin(flow2, dimX, dimY, 2, 1, u, v) * (float)s);
+            float shx = roundf(tex_lin(flow2, dimX, dimY, 2, 0, u, v) * sf);
+            float shy = roundf(tex_lin(flow2, dimX, dimY, 2, 1, u, v) * sf);
             int sx = (int)shx, sy = (int)shy;
             for (int py = -2; py <= 2; py++)
                 for (int px = -2; px <= 2; px++) {
                     int ppsx = X + px + sx, ppsy = Y + py + sy, ppx = X + px, ppy = Y + py;
-                    ppsx = mini(maxi(ppsx / s, g->clamp_x0), g->clamp_x1);
-                    ppsy = mini(maxi(ppsy / s, g->clamp_y0), g->clamp_y1);
-                    ppx = mini(maxi(ppx / s, g->clamp_x0), g->clamp_x1);
-                    ppy = mini(maxi(ppy / s, g->clamp_y0), g->clamp_y1);
+                    ppsx = mini(maxi(ppsx * den / s, g->clamp_x0), g->clamp_x1);
+                    ppsy = mini(maxi(ppsy * den / s, g->clamp_y0), g->clamp_y1);
+                    ppx = mini(maxi(ppx * den / s, g->clamp_x0), g->clamp_x1);
+                    ppy = mini(maxi(ppy * den / s, g->clamp_y0), g->clamp_y1);
                     int col = cfa[(ppsy % 2) * 2 + (ppsx % 2)];
                     float w = px * px * kx + 2 * px * py * kz + py * py * ky;
                     w = expf(-0.5f * w);
@@ -948,7 +951,8 @@ void orc_fallback_upsample(const float* rgb3, int w, int h, float* out3, const o
 #pragma omp parallel for schedule(static)
     for (int y = 0; y < g->out_h; y++)
         for (int x = 0; x < g->out_w; x++) {
-            float u = ((float)(x + g->org_x) + 0.5f) / (float)g->scale, v = ((float)(y + g->org_y) + 0.5f) / (float)g->scale;
+            const int num = g->scale & 0xffff, den = ((g->scale >> 16) & 0xffff) ? ((g->scale >> 16) & 0xffff) : 1;
+            float u = (((float)(x + g->org_x) + 0.5f) * (float)den) / (float)num, v = (((float)(y + g->org_y) + 0.5f) * (float)den) / (float)num;
             for (int c = 0; c < 3; c++) out3[3 * ((size_t)y * g->out_w + x) + c] = tex_lin(rgb3, w, h, 3, c, u, v);
         }
 }

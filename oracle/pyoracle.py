@@ -28,7 +28,8 @@ class Geom(C.Structure):
 
     @classmethod
     def full_frame(cls, w, h, s):
-        return cls(w, h, s, w * s, h * s, 0, 0, 0, w - 1, 0, h - 1)
+        num, den = s & 0xffff, ((s >> 16) & 0xffff) or 1          # include/mfsr.h MFSR_SCALE_RATIONAL
+        return cls(w, h, s, w * num // den, h * num // den, 0, 0, 0, w - 1, 0, h - 1)
 
     @classmethod
     def from_product(cls, g):

@@ -56,6 +56,28 @@ def test_merge_full_frame_scales_vs_oracle(cuda_device, scale):
     assert max_abs(out, exp) <= TOL_MAXABS and psnr(out, exp) >= TOL_PSNR
 
 
+def test_merge_rational_scale_vs_oracle(cuda_device):
+    """1.5x (MFSR_SCALE_RATIONAL(3, 2)): every "/ s" of the tap arithmetic becomes "* den / num"; and num / 1 is the integer scale, bit for bit."""
+    from multi_frame_super_resolution_b200._lib import scale_rational
+    n, h, w = 4, 64, 96
+    raw, mask, flow, kern, g = _inputs(n, h, w, 91, cuda_device)
+    geom = MergeGeom.full_frame(w, h, scale_rational(3, 2))
+    assert (geom.out_w, geom.out_h) == (144, 96)
+    fb = torch.rand((geom.out_h, geom.out_w, 3), generator=g)
+    out, s, wt, exp, es, ew = _run_both(raw, mask, flow, kern, fb, geom, cuda_device)
+    assert max_abs(out, exp) <= TOL_MAXABS and psnr(out, exp) >= TOL_PSNR
+    assert np.allclose(s, es, rtol=2e-5, atol=2e-5) and np.allclose(wt, ew, rtol=2e-5, atol=2e-5)
+    assert float(wt.max()) > 0.5                                   # the taps did land on samples
+    # 3 / 1 through the rational path of the plain loop == scale 3 (lean loop) within the merge tolerance
+    g3, g31 = MergeGeom.full_frame(w, h, 3), MergeGeom.full_frame(w, h, scale_rational(3, 1))
+    fb3 = torch.rand((g3.out_h, g3.out_w, 3), generator=g)
+    a = stages.merge(raw.to(cuda_device), mask.to(cuda_device), flow.to(cuda_device), kern.to(cuda_device), fb3.to(cuda_device), g3, WHITE, BLACK, 0.1)
+    b = stages.merge(raw.to(cuda_device), mask.to(cuda_device), flow.to(cuda_device), kern.to(cuda_device), fb3.to(cuda_device), g31, WHITE, BLACK, 0.1)
+    a = a[0] if isinstance(a, tuple) else a
+    b = b[0] if isinstance(b, tuple) else b
+    assert max_abs(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5
+
+
 def test_merge_lean_kernel_large_shifts_and_bad_certainties(cuda_device):
     """Scale 3 (merge_lean_kernel) with large shifts (taps run into the clamp range) and non-finite certainties, against the oracle's
     tap loop, accumulators included."""

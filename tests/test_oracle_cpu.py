@@ -145,3 +145,25 @@ def test_bundled_burst_config1_prealigned():
         assert np.median(np.hypot(ts[:, 0], ts[:, 1])) < (1.5 if f < 4 else 3.0), f
         assert it["mask"][f][..., :3].mean() > 0.4, (f, it["mask"][f][..., :3].mean())
     assert np.isfinite(out).all()
+
+
+def test_oracle_rational_scale_reduces_to_integer():
+    """include/mfsr.h MFSR_SCALE_RATIONAL: num / 1 is the reference's integer arithmetic bit for bit; 3 / 2 gives a 1.5x grid."""
+    rng = np.random.default_rng(7)
+    n, h, w = 2, 32, 48
+    raw = rng.integers(64, 1023, (n, h, w)).astype(np.uint16)
+    mask = rng.random((n, h // 2, w // 2, 4)).astype(np.float32)
+    flow = ((rng.random((n, h, w, 2)) - 0.5) * 4).astype(np.float32)
+    kern = np.zeros((h, w, 4), np.float32); kern[..., 0] = 0.5; kern[..., 1] = 0.5
+    white, black = [959.0] * 3, [64.0] * 3
+    outs = []
+    for s in (2, (1 << 16) | 2):
+        g = O.Geom.full_frame(w, h, s)
+        fb = np.full((g.out_h, g.out_w, 3), 0.25, np.float32)
+        outs.append(O.merge(raw, mask, flow, kern, fb, g, white, black, 0.1, [0, 1, 1, 2]))
+    assert np.array_equal(outs[0], outs[1])
+    g = O.Geom.full_frame(w, h, (2 << 16) | 3)
+    assert (g.out_w, g.out_h) == (72, 48)
+    fb = np.full((g.out_h, g.out_w, 3), 0.25, np.float32)
+    out = O.merge(raw, mask, flow, kern, fb, g, white, black, 0.1, [0, 1, 1, 2])
+    assert out.shape == (48, 72, 3) and np.isfinite(out).all() and out[1:-1, 1:-1].std() > 0.01

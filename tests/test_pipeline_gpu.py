@@ -300,3 +300,29 @@ def test_pipeline_config2_full_size_vs_oracle(cuda_device):
         assert np.array_equal(sr.tile_shifts(f), it["frame_shift"][f])
     _compare_images(out, exp)
     sr.close()
+
+
+def test_pipeline_rational_scale_1p5(cuda_device):
+    """s = 1.5 (MFSR_SCALE_RATIONAL(3, 2)) through the whole chain against the oracle; rejected where it is not defined."""
+    from multi_frame_super_resolution_b200._lib import MfsrError, scale_rational
+    fr, _ = synth_burst(4, 128, 192, seed=17)
+    p = default_params()
+    p.levels = 2
+    p.scale = scale_rational(3, 2)
+    sr = BurstSuperResolution(p, 0, 192, 128, 4)
+    assert sr.output_size(192, 128) == (288, 192)
+    sr.set_input(fr.to(cuda_device))
+    out = sr.next_frame().cpu().numpy()
+    exp, _ = O.run_pipeline(u16(fr), p)
+    assert out.shape == exp.shape == (192, 288, 3)
+    _compare_images(out, exp)
+    sr.close()
+    q = default_params()
+    q.scale = scale_rational(3, 2)
+    q.full_frame = 0                                  # the reference's central crop is defined for integer scales only
+    with pytest.raises(MfsrError):
+        BurstSuperResolution(q, 0, 192, 128, 4).workspace_bytes
+    q = default_params()
+    q.scale = scale_rational(9, 2)                    # 4.5x: beyond the supported range
+    with pytest.raises(MfsrError):
+        BurstSuperResolution(q, 0, 192, 128, 4).workspace_bytes
