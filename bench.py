@@ -439,10 +439,33 @@ def bench_rowband(args, rank, world, local_rank, numa):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # halo rows straight out of the neighbours' memory over NVLink (torch symmetric memory); grouped ncclSend/ncclRecv where that is not available
+    peer, transport = None, "none (one rank)"
+    if world > 1:
+        transport = "nccl grouped send/recv"
+        if os.environ.get("MFSR_HALO", "peer") == "peer":
+            try:
+                peer = rowband.PeerHaloExchange(N, bands, rank, W * 2, dev)
+                transport = "peer memory over NVLink (torch symmetric memory), device-side barriers"
+            except Exception as e:              # noqa: BLE001  (no symmetric memory on this box: the NCCL exchange is the same data)
+                transport = f"nccl grouped send/recv (symmetric memory unavailable: {type(e).__name__})"
+        flag = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)       # all ranks or none
+        if int(flag.item()) == 0:
+            peer = None
+        if peer is not None:                              # the rank's own rows live in the shared band buffer from now on
+            peer.own_view().copy_(own)
+            own = peer.own_view()
+
     def step():
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
-        banded = rowband.exchange_halos(own, bands, rank) if world > 1 else own
+        if world == 1:
+            banded = own
+        elif peer is not None:
+            banded = peer.exchange()
+        else:
+            banded = rowband.exchange_halos(own, bands, rank)
         e1.record()
         sr.set_input(banded)
         sr.next_frame(out=out)
@@ -473,11 +496,17 @@ def bench_rowband(args, rank, world, local_rank, numa):
     # e2e: own rows from pinned host memory, exchange, chain, 8-bit band result to pinned host memory
     host_own = torch.empty((N, b.rows, W), dtype=torch.int16, pin_memory=True); host_own.copy_(own)
     host_out = torch.empty((oh, ow, 3), dtype=torch.uint8, pin_memory=True)
-    own2 = torch.empty_like(own)
+    own2 = own if peer is not None else torch.empty_like(own)
 
     def step_e2e():
-        own2.copy_(host_own, non_blocking=True)
-        banded = rowband.exchange_halos(own2, bands, rank) if world > 1 else own2
+        for f in range(N):                                # one dense copy per frame (own2 may be a strided view of the band buffer)
+            own2[f].copy_(host_own[f], non_blocking=True)
+        if world == 1:
+            banded = own2
+        elif peer is not None:
+            banded = peer.exchange()
+        else:
+            banded = rowband.exchange_halos(own2, bands, rank)
         sr.set_input(banded)
         sr.next_frame(out=host_out, host=True, sync=True, dtype=torch.uint8)
 
@@ -497,7 +526,7 @@ def bench_rowband(args, rank, world, local_rank, numa):
     if args.verify:
         if world > 1:
             parts = [torch.empty((2 * x.rows, 2 * W, 3), dtype=torch.float32, device=dev) for x in bands] if rank == 0 else None
-            sr.set_input(rowband.exchange_halos(own, bands, rank)); sr.next_frame(out=out); sr.synchronize()
+            sr.set_input(peer.exchange() if peer is not None else rowband.exchange_halos(own, bands, rank)); sr.next_frame(out=out); sr.synchronize()
             dist.gather(out, parts, dst=0)
             stitched = torch.cat(parts, 0) if rank == 0 else None
         else:
@@ -517,9 +546,9 @@ def bench_rowband(args, rank, world, local_rank, numa):
                 "mode": "rowband",
                 "config": {"workload": f"ONE synthetic {W}x{H} RGGB burst, {N} frames, 2x, full frame, split into {world} row band(s)",
                            "frames": N, "raw": [W, H], "scale": 2, "bursts_per_step": 1,
-                           "parallelism": f"row bands x{world}: halo rows of the raw frames exchanged by grouped ncclSend/ncclRecv (the only exchange step), then the unmodified chain per band",
+                           "parallelism": f"row bands x{world}: halo rows of the raw frames exchanged between neighbours (the only exchange step; transport in halo.transport), then the unmodified chain per band",
                            "l2": "inputs larger than L2"},
-                "halo": {"ms_exchange": round(float(np.mean(halo)), 3), "rows": rowband.DEFAULT_HALO, "margin_rows": margin,
+                "halo": {"ms_exchange": round(float(np.mean(halo)), 3), "transport": transport, "rows": rowband.DEFAULT_HALO, "margin_rows": margin,
                          "bytes_received_per_rank": int((b.halo_up + b.halo_down) * W * 2 * N), "band_rows": [x.rows for x in bands],
                          "processed_rows": [x.bottom - x.top for x in bands]},
                 "e2e": {"value": round(out_mp / (e2e_ms / 1e3), 2), "unit": UNIT, "ms_per_step": round(e2e_ms, 3), "h2d_bytes_per_step": int(N * H * W * 2),

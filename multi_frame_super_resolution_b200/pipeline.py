@@ -165,14 +165,19 @@ class BurstSuperResolution:
             n, h, w = frames.shape
             base, on_host = frames.ctypes.data, 1
         else:
-            if frames.dim() != 3 or frames.element_size() != 2 or not frames.is_contiguous():
-                raise ValueError("frames must be a contiguous 16-bit tensor [N,H,W]")
+            # every frame dense ([H,W] contiguous); the frames themselves may be further apart than H*W (a view into a larger stack)
+            if frames.dim() != 3 or frames.element_size() != 2 or frames.stride(2) != 1 or frames.stride(1) != frames.shape[2] or \
+                    (frames.shape[0] > 1 and frames.stride(0) < frames.shape[1] * frames.shape[2]):
+                raise ValueError("frames must be a 16-bit tensor [N,H,W] with dense frames")
             n, h, w = frames.shape
             base, on_host = frames.data_ptr(), 0 if frames.is_cuda else 1
+            fstride = frames.stride(0) * 2 if n > 1 else h * w * 2
         if not on_host:
             # the frames were produced on torch's current stream: order the handle's stream after it
             self._ext().wait_stream(torch.cuda.current_stream(self.device))
-        ptrs = (C.c_void_p * n)(*[base + i * h * w * 2 for i in range(n)])
+        if isinstance(frames, np.ndarray):
+            fstride = h * w * 2
+        ptrs = (C.c_void_p * n)(*[base + i * fstride for i in range(n)])
         old = self._keep
         if isinstance(old, torch.Tensor) and old.is_cuda:
             # device frames are read in place until the end of the run: their memory must not go back to the caching allocator

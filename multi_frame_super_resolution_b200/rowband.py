@@ -2,8 +2,9 @@
 
 Every rank owns a contiguous band of raw rows of all N frames.  The only exchange step of the path is the halo: the
 rows a band needs from its neighbours so that every stage (coarsest-level tile matching has the largest footprint)
-sees true data around the rows it keeps.  Halo rows travel by NCCL send/recv over NVLink (`exchange_halos`, one grouped
-batch per direction); after that each rank runs the unmodified chain on band + halo in row-band mode
+sees true data around the rows it keeps.  Halo rows are copied out of the neighbours' memory over NVLink (`PeerHaloExchange`,
+torch symmetric memory) or travel by NCCL send/recv (`exchange_halos`, one grouped batch per direction: also the gloo / CPU test
+path); after that each rank runs the unmodified chain on band + halo in row-band mode
 (`mfsr_params.band_*`), which maps tile rows through the full frame's coordinates and merges only the kept rows.
 No other collective touches the data path.
 
@@ -110,6 +111,53 @@ def exchange_halos(own: torch.Tensor, bands: List[Band], rank: int, group=None) 
         else:
             out[:, b.halo_up + rows:] = recv
     return out.view(dtype)
+
+
+class PeerHaloExchange:
+    """The same exchange without a collective library on the data path.  The band buffer of every rank (own rows + halo rows of all
+    frames) is allocated in torch's symmetric memory, i.e. mapped into every peer of the node; the rank's own rows are written
+    straight into it (own_view()), and exchange() copies the halo rows out of the neighbours' buffers over NVLink / NVSwitch — one
+    contiguous device-to-device copy per frame and neighbour, between two device-side barriers — and returns the band.  No staging
+    copy of the own rows, no send / receive buffers.  The band buffer is reused by the next burst: the consumer of exchange()'s
+    result (the handle reads it in place) has to be finished before own_view() is written again.
+    Raises whatever torch raises where symmetric memory is not available (single GPU, gloo, no P2P): callers fall back to
+    exchange_halos()."""
+
+    def __init__(self, n_frames: int, bands: List[Band], rank: int, width_bytes: int, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.bands, self.rank, self.n, self.wb = bands, rank, n_frames, width_bytes
+        self.rows_max = max(b.bottom - b.top for b in bands)
+        self.buf = symm.empty((n_frames, self.rows_max, width_bytes), dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+
+    def own_view(self, dtype=torch.int16) -> torch.Tensor:
+        """[N, band.rows, W]: where the rank's own rows go (frames are rows_max rows apart)."""
+        b = self.bands[self.rank]
+        return self.buf[:, b.halo_up:b.halo_up + b.rows].view(dtype)
+
+    def band_view(self, dtype=torch.int16) -> torch.Tensor:
+        b = self.bands[self.rank]
+        return self.buf[:, :b.bottom - b.top].view(dtype)
+
+    def exchange(self, dtype=torch.int16) -> torch.Tensor:
+        """Own rows are in own_view().  Returns [N, band + halo rows, W] (a view: each frame dense, frames rows_max rows apart)."""
+        b = self.bands[self.rank]
+        shape = (self.n, self.rows_max, self.wb)
+        self.hdl.barrier(channel=0)                  # every rank's own rows are in place
+        if self.rank > 0:
+            up = self.bands[self.rank - 1]
+            peer = self.hdl.get_buffer(self.rank - 1, shape, torch.uint8)
+            lo = up.halo_up + up.rows - b.halo_up
+            for f in range(self.n):
+                self.buf[f, :b.halo_up].copy_(peer[f, lo:lo + b.halo_up], non_blocking=True)
+        if self.rank < len(self.bands) - 1:
+            dn = self.bands[self.rank + 1]
+            peer = self.hdl.get_buffer(self.rank + 1, shape, torch.uint8)
+            for f in range(self.n):
+                self.buf[f, b.halo_up + b.rows:b.bottom - b.top].copy_(peer[f, dn.halo_up:dn.halo_up + b.halo_down], non_blocking=True)
+        self.hdl.barrier(channel=1)                  # every rank has read: own rows may take the next burst
+        return self.band_view(dtype)
 
 
 def band_params(params, band: Band, global_height: int, margin=None):

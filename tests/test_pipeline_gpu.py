@@ -326,3 +326,24 @@ def test_pipeline_rational_scale_1p5(cuda_device):
     q.scale = scale_rational(9, 2)                    # 4.5x: beyond the supported range
     with pytest.raises(MfsrError):
         BurstSuperResolution(q, 0, 192, 128, 4).workspace_bytes
+
+
+def test_set_input_accepts_a_view_with_a_larger_frame_stride(cuda_device):
+    """Frames that are dense but further apart than H*W (a row band inside the shared band buffer of rowband.PeerHaloExchange) are used
+    in place and give the image of the dense stack, bit for bit; rows that are not dense are rejected."""
+    n, h, w = 3, 128, 192
+    fr, _ = synth_burst(n, h, w, seed=23)
+    p = default_params()
+    p.levels = 2
+    sr = BurstSuperResolution(p, 0, w, h, n)
+    sr.set_input(fr.to(cuda_device))
+    ref = sr.next_frame().clone()
+    big = torch.zeros((n, h + 40, w), dtype=fr.dtype, device=cuda_device)
+    big[:, 8:8 + h] = fr.to(cuda_device)
+    view = big[:, 8:8 + h]
+    assert not view.is_contiguous()
+    sr.set_input(view)
+    assert torch.equal(sr.next_frame(), ref)
+    with pytest.raises(ValueError):
+        sr.set_input(big[:, :h, :w - 2])
+    sr.close()
