@@ -40,6 +40,22 @@ for (name, n, h, w, scale, ms, fmt) in (('config5 4K x30 3x', 30, 2160, 3840, 3,
           '99th pct', round(float(np.percentile(err, 99)), 3), flush=True)
     print(name, {k: round(v, 2) for k, v in st.items()}, 'sum', round(sum(st.values()), 2), 'MP/s', round(ow * oh / 1e6 / (sum(st.values()) / 1e3)),
           'back-to-back ms/burst', round(per, 3), 'launches', sr.launch_count(), flush=True)
+    if n <= 8:
+        # the same bursts on several handles (one stream each) issued round-robin: kernels of different bursts overlap and fill the
+        # tails of the small grids
+        import time
+        for nh in (2, 3):
+            hs = [BurstSuperResolution(p, device=0, max_width=w, max_height=h, max_frames=n) for _ in range(nh)]
+            outs = [torch.empty((oh, ow, 3), dtype=torch.float32, device=dev) for _ in range(nh)]
+            for k in range(2 * nh):
+                hs[k % nh].set_input(fr, fmt=fmt); hs[k % nh].next_frame(out=outs[k % nh])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for k in range(reps):
+                hs[k % nh].set_input(fr, fmt=fmt); hs[k % nh].next_frame(out=outs[k % nh])
+            torch.cuda.synchronize()
+            print(name, f'{nh} handles round-robin: ms/burst', round((time.perf_counter() - t0) * 1e3 / reps, 3), flush=True)
+            for x in hs: x.close()
     sr.close(); del fr, out
 if '--all' not in sys.argv:
     sys.exit(0)
