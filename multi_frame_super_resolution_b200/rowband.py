@@ -131,6 +131,16 @@ class PeerHaloExchange:
         self.buf = symm.empty((n_frames, self.rows_max, width_bytes), dtype=torch.uint8, device=device)
         self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
 
+    @classmethod
+    def from_handle(cls, buf: torch.Tensor, hdl, bands: List[Band], rank: int):
+        """An exchange over an existing buffer + peer handle (anything with get_buffer(rank, sizes, dtype) and barrier(channel=...)):
+        what __init__ builds from torch's symmetric memory; the CPU tests pass a stand-in that hands out the other ranks' buffers."""
+        self = cls.__new__(cls)
+        self.bands, self.rank, self.n, self.wb = bands, rank, buf.shape[0], buf.shape[2]
+        self.rows_max = buf.shape[1]
+        self.buf, self.hdl = buf, hdl
+        return self
+
     def own_view(self, dtype=torch.int16) -> torch.Tensor:
         """[N, band.rows, W]: where the rank's own rows go (frames are rows_max rows apart)."""
         b = self.bands[self.rank]

@@ -54,3 +54,33 @@ def test_halo_exchange_gloo(world):
         assert p.exitcode == 0
     assert [r[0] for r in res] == list(range(world))
     assert all(r[1] for r in res), res
+
+
+def test_peer_halo_exchange_indexing():
+    """rowband.PeerHaloExchange: every rank reads its halo rows out of the neighbours' band buffers (own rows sit behind the neighbour's
+    own upper halo).  The peer mapping is replaced by a stand-in that hands out the other ranks' buffers; 3 bands, uneven last band."""
+    import torch
+    from multi_frame_super_resolution_b200 import rowband
+
+    n, H, W = 2, 128 * 7, 24
+    full = torch.arange(n * H * W, dtype=torch.int32).remainder(30011).to(torch.int16).reshape(n, H, W)
+    bands = rowband.plan_bands(H, 3, 128, 256)
+    rows_max = max(b.bottom - b.top for b in bands)
+    bufs = [torch.zeros((n, rows_max, W * 2), dtype=torch.uint8) for _ in bands]
+
+    class Hdl:
+        def get_buffer(self, rank, sizes, dtype):
+            assert tuple(sizes) == tuple(bufs[rank].shape) and dtype == torch.uint8
+            return bufs[rank]
+
+        def barrier(self, channel=0):
+            pass
+
+    ex = [rowband.PeerHaloExchange.from_handle(bufs[r], Hdl(), bands, r) for r in range(3)]
+    for r, b in enumerate(bands):
+        ex[r].own_view().copy_(full[:, b.row0:b.row1])
+    for r, b in enumerate(bands):
+        got = ex[r].exchange()
+        assert got.shape == (n, b.bottom - b.top, W) and got.dtype == torch.int16
+        assert torch.equal(got, full[:, b.top:b.bottom]), r
+        assert all(got[f].is_contiguous() for f in range(n))            # dense frames, a larger frame stride: what set_input accepts
