@@ -347,3 +347,38 @@ def test_set_input_accepts_a_view_with_a_larger_frame_stride(cuda_device):
     with pytest.raises(ValueError):
         sr.set_input(big[:, :h, :w - 2])
     sr.close()
+
+
+def test_pipeline_config5_large_motion_prealigned(cuda_device):
+    """Config 5's regime on a small image: inter-frame motion beyond the pyramid matcher's reach (max_shift * (2^levels - 1) = 28 px at
+    3 levels; the frames move up to +-24 px each, i.e. up to 48 px against each other), 3x scale.  Without the global pre-alignment the
+    flows are garbage; with it the CUDA chain equals the oracle's (poses, integer shifts, consolidated shifts bit-exact; image 1e-3 /
+    60 dB) and the recovered flow is within 1 px of the truth at the median ("config 5 aligned with a parity test")."""
+    n, h, w = 6, 320, 448
+    fr, sh = synth_burst(n, h, w, seed=515, max_shift=24.0)
+    p = default_params()
+    p.scale = 3
+    p.levels = 3
+    p.pair_span = 1
+    errs = {}
+    for pre in (0, 1):
+        p.prealign = pre
+        sr, out = _run(p, fr, cuda_device, ref_idx=0)
+        e = []
+        for f in range(1, n):
+            fl = sr.buffer("flow", h, w * 8, f).view(np.float32).reshape(h, w, 2)[h // 4:3 * h // 4:4, w // 4:3 * w // 4:4]
+            e.append(np.abs(fl + sh[f].numpy()[None, None, :]).max(-1).ravel())
+        errs[pre] = float(np.median(np.concatenate(e)))
+        if pre:
+            exp, it = O.run_pipeline(u16(fr), p, ref_idx=0, keep=True)
+            assert np.array_equal(sr.buffer("pose", n, 16).view(np.float32).reshape(n, 4), np.stack(it["poses"]))
+            for k in range(sr.tile_grid()[2]):
+                assert np.array_equal(sr.tile_argmin(k), it["argmin"][k]), f"pair {k}"
+            for f in range(n):
+                assert np.array_equal(sr.tile_shifts(f), it["frame_shift"][f])
+            # the LK flows of the two sides differ by ~1e-3 px (MUFU sqrt / rcp, re-associated sums); at 3x a sample whose 3 * flow sits
+            # within that of a rounding boundary reads a neighbouring raw sample: isolated flips (measured 4.7e-4 of the samples), not drift
+            _compare_images(out, exp, frac=1.5e-3, db=45.0)
+        sr.close()
+    assert errs[1] < 1.0, errs
+    assert errs[0] > 4.0, errs          # the reach really is exceeded without it
