@@ -23,6 +23,20 @@ flow_from_tiles_kernel(const float2* __restrict__ tiles, int64_t tile_pitch, int
     tiles = frame_ptr(tiles, tiles_fs, blockIdx.z);      // blockIdx.z = frame
     flow = frame_ptr(flow, flow_fs, blockIdx.z);
     if (frame_pose) { frame_pose += 4 * blockIdx.z; bsx = frame_pose[0]; bsy = frame_pose[1]; cr = frame_pose[2]; sr = frame_pose[3]; }      // prealign.cu
+    // the row part of the bilinear tile fetch (texture row, fraction, clamped tile rows) is the same for every pixel of a row: the
+    // block's 64 rows are worked out once, by 64 threads, instead of once per pixel (an IEEE division + tex_axis + clamps, ~30 of the
+    // ~70 instructions per pixel); the per-pixel arithmetic is unchanged, the flow field bit-identical
+    __shared__ int s_i0[8 * FFT_ROWS], s_i1[8 * FFT_ROWS];
+    __shared__ float s_a[8 * FFT_ROWS];
+    {
+        const int t = threadIdx.y * blockDim.x + threadIdx.x;
+        if (t < 8 * FFT_ROWS) {
+            const int y = blockIdx.y * 8 * FFT_ROWS + t;
+            TexAxis ay = tex_axis(tex_coord((float)(min(y, h - 1) + gy0) + 0.5f, gh, gty), gty);
+            s_i0[t] = clampi(ay.i0 - trow0, 0, tilesY - 1); s_i1[t] = clampi(ay.i1 - trow0, 0, tilesY - 1); s_a[t] = ay.a;
+        }
+    }
+    __syncthreads();
     const int x = blockIdx.x * blockDim.x + threadIdx.x, yb = (blockIdx.y * blockDim.y + threadIdx.y) * FFT_ROWS;
     if (x >= w || yb >= h) return;
     const float bx = cr * -bsx - sr * -bsy, by = sr * -bsx + cr * -bsy;
@@ -36,12 +50,13 @@ flow_from_tiles_kernel(const float2* __restrict__ tiles, int64_t tile_pitch, int
         const float pcy = (float)(y + gy0 - gh / 2);
         sx += cr * pcx - sr * pcy - pcx;
         sy += sr * pcx + cr * pcy - pcy;
-        TexAxis ay = tex_axis(tex_coord((float)(y + gy0) + 0.5f, gh, gty), gty);
-        ay.i0 = clampi(ay.i0 - trow0, 0, tilesY - 1); ay.i1 = clampi(ay.i1 - trow0, 0, tilesY - 1);
-        const float2 t00 = row_ptr(tiles, tile_pitch, ay.i0)[ax.i0], t10 = row_ptr(tiles, tile_pitch, ay.i0)[ax.i1];
-        const float2 t01 = row_ptr(tiles, tile_pitch, ay.i1)[ax.i0], t11 = row_ptr(tiles, tile_pitch, ay.i1)[ax.i1];
-        sx += tex_mix(t00.x, t10.x, t01.x, t11.x, ax.a, ay.a);
-        sy += tex_mix(t00.y, t10.y, t01.y, t11.y, ax.a, ay.a);
+        const int rl = threadIdx.y * FFT_ROWS + r;
+        const int i0 = s_i0[rl], i1 = s_i1[rl];
+        const float aya = s_a[rl];
+        const float2 t00 = row_ptr(tiles, tile_pitch, i0)[ax.i0], t10 = row_ptr(tiles, tile_pitch, i0)[ax.i1];
+        const float2 t01 = row_ptr(tiles, tile_pitch, i1)[ax.i0], t11 = row_ptr(tiles, tile_pitch, i1)[ax.i1];
+        sx += tex_mix(t00.x, t10.x, t01.x, t11.x, ax.a, aya);
+        sy += tex_mix(t00.y, t10.y, t01.y, t11.y, ax.a, aya);
         row_ptr(flow, flow_pitch, y)[x] = make_float2(sx, sy);
     }
 }
