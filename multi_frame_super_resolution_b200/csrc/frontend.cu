@@ -424,22 +424,35 @@ __global__ void __launch_bounds__(256)
 fallback_upsample_kernel(const float* __restrict__ rgb, int64_t rgb_pitch, int w, int h,
                          float* __restrict__ out, int64_t out_pitch, mfsr_merge_geom g)
 {
+    // row part of the bilinear fetch once per block row (64 rows per block), as in flow_from_tiles_kernel; per-pixel arithmetic unchanged
+    __shared__ int s_i0[8 * FBU_ROWS], s_i1[8 * FBU_ROWS];
+    __shared__ float s_a[8 * FBU_ROWS];
+    const float fs = (float)MFSR_SCALE_NUM(g.scale), fd = (float)MFSR_SCALE_DEN(g.scale);      // ((X + 0.5) * den) / num; den == 1: exact factor
+    {
+        const int t = threadIdx.y * blockDim.x + threadIdx.x;
+        if (t < 8 * FBU_ROWS) {
+            const int y = min((int)blockIdx.y * 8 * FBU_ROWS + t, g.out_h - 1);
+            const TexAxis ty = tex_axis(__fdiv_rn(__fmul_rn((float)(y + g.org_y) + 0.5f, fd), fs), h);
+            s_i0[t] = ty.i0; s_i1[t] = ty.i1; s_a[t] = ty.a;
+        }
+    }
+    __syncthreads();
     const int x = blockIdx.x * blockDim.x + threadIdx.x, yb = (blockIdx.y * blockDim.y + threadIdx.y) * FBU_ROWS;
     if (x >= g.out_w || yb >= g.out_h) return;
-    const float fs = (float)MFSR_SCALE_NUM(g.scale), fd = (float)MFSR_SCALE_DEN(g.scale);      // ((X + 0.5) * den) / num; den == 1: exact factor
     const TexAxis tx = tex_axis(__fdiv_rn(__fmul_rn((float)(x + g.org_x) + 0.5f, fd), fs), w);
     const int o0 = 3 * tx.i0, o1 = 3 * tx.i1;
 #pragma unroll 2
     for (int r = 0; r < FBU_ROWS; r++) {
         const int y = yb + r;
         if (y >= g.out_h) break;
-        const TexAxis ty = tex_axis(__fdiv_rn(__fmul_rn((float)(y + g.org_y) + 0.5f, fd), fs), h);
-        const float* r0 = row_ptr(rgb, rgb_pitch, ty.i0);
-        const float* r1 = row_ptr(rgb, rgb_pitch, ty.i1);
+        const int rl = threadIdx.y * FBU_ROWS + r;
+        const float* r0 = row_ptr(rgb, rgb_pitch, s_i0[rl]);
+        const float* r1 = row_ptr(rgb, rgb_pitch, s_i1[rl]);
+        const float tya = s_a[rl];
         float* o = row_ptr(out, out_pitch, y) + 3 * x;
 #pragma unroll
         for (int c = 0; c < 3; c++)
-            o[c] = tex_mix(__ldg(r0 + o0 + c), __ldg(r0 + o1 + c), __ldg(r1 + o0 + c), __ldg(r1 + o1 + c), tx.a, ty.a);
+            o[c] = tex_mix(__ldg(r0 + o0 + c), __ldg(r0 + o1 + c), __ldg(r1 + o0 + c), __ldg(r1 + o1 + c), tx.a, tya);
     }
 }
 
