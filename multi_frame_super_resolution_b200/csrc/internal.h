@@ -56,7 +56,8 @@ int launch_pyramid_down(const uint8_t* in, int64_t in_pitch, int64_t in_fs, int 
                         cudaStream_t stream);
 int launch_robustness(const float* rgb_ref, const float* rgb_mov, int64_t rgb_pitch, int64_t rgb_fs, const float* flow, int64_t flow_pitch,
                       int64_t flow_fs, float* mask, int64_t mask_pitch, int64_t mask_fs, float* scratch, int64_t scratch_fs, int frames,
-                      int w, int h, float alpha, float beta, float thresholdM, int erode_radius, cudaStream_t st);
+                      int w, int h, float alpha, float beta, float thresholdM, int erode_radius, cudaStream_t st,
+                      float* ref_stats = nullptr);      // ref_stats: w * h * 6 floats of scratch: the reference part of the certainty computed once
 
 // global pre-alignment (prealign.cu)
 int launch_prealign_stage(const uint8_t* img, int64_t pitch, int64_t frame_stride, int w, int h, int n_frames, int ref_idx,

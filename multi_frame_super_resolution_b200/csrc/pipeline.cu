@@ -51,7 +51,7 @@ struct mfsr_context {
     float* gray; int64_t gray_pitch, gray_fs;
     float* rgb_ref; int64_t rgb_pitch;
     float2* flowA; float2* flowB; int64_t flow_pitch, flow_fs;
-    float4* mask; int64_t mask_pitch, mask_fs;
+    float4* mask; int64_t mask_pitch, mask_fs; float* rstats;
     float4* kern; int64_t kern_pitch;
     float* fallback; float* outbuf; int64_t out_pitch_own;
     float* part_sum; float* part_weight;               // partial sums of the frame-chunked merge (bursts of more than 10 frames), else null
@@ -244,6 +244,7 @@ static size_t carve(mfsr_context* c, char* base, int n, int w, int h)
     c->flowB = (float2*)take((size_t)c->flow_fs * n);
     c->mask_pitch = (int64_t)hw * 16; c->mask_fs = c->mask_pitch * hh;
     c->mask = (float4*)take((size_t)c->mask_fs * n);
+    c->rstats = (float*)take((size_t)hw * hh * 24);            // reference patch statistics of the robustness model (6 floats per half-res pixel)
     c->kern_pitch = (int64_t)w * 16;
     c->kern = (float4*)take((size_t)c->kern_pitch * h);
     mfsr_merge_geom g; make_geom(p, w, h, &g);
@@ -597,7 +598,8 @@ static int run_impl(mfsr_handle h, void* out_any, int64_t out_pitch, int out_on_
                           (const float*)((const char*)h->rgb_half + h->rgbh_pitch * (ra / 2)), h->rgbh_pitch, h->rgbh_fs,
                           (const float*)((const char*)cur + h->flow_pitch * ra), h->flow_pitch, h->flow_fs,
                           (float*)((char*)h->mask + h->mask_pitch * (ra / 2)), h->mask_pitch, h->mask_fs,
-                          nullptr, 0, n, hw2, rh / 2, p.alpha, p.beta, p.thresholdM, p.mask_erode_radius, st));
+                          nullptr, 0, n, hw2, rh / 2, p.alpha, p.beta, p.thresholdM, p.mask_erode_radius, st, h->rstats));
+    h->launches += 1;
     // ---- fallback image (ApplyWeighting's inOutImg): demosaiced reference on the output grid
     MFSR_CUDA_TRY(cudaEventRecord(h->ev[ST_FALLBACK], st));
     // Row-band mode: the reference leaves the 1-pixel border of the merge WINDOW untouched (DeBayerKernels.cu:391).  At an
