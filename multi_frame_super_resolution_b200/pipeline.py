@@ -163,7 +163,7 @@ class BurstSuperResolution:
             if frames.dtype != np.uint16 or frames.ndim != 3 or not frames.flags.c_contiguous:
                 raise ValueError("host frames must be a C-contiguous uint16 array [N,H,W]")
             n, h, w = frames.shape
-            base, on_host = frames.ctypes.data, 1
+            base, on_host, fstride = frames.ctypes.data, 1, h * w * 2
         else:
             # every frame dense ([H,W] contiguous); the frames themselves may be further apart than H*W (a view into a larger stack)
             if frames.dim() != 3 or frames.element_size() != 2 or frames.stride(2) != 1 or frames.stride(1) != frames.shape[2] or \
@@ -175,8 +175,6 @@ class BurstSuperResolution:
         if not on_host:
             # the frames were produced on torch's current stream: order the handle's stream after it
             self._ext().wait_stream(torch.cuda.current_stream(self.device))
-        if isinstance(frames, np.ndarray):
-            fstride = h * w * 2
         ptrs = (C.c_void_p * n)(*[base + i * fstride for i in range(n)])
         old = self._keep
         if isinstance(old, torch.Tensor) and old.is_cuda:
